@@ -1,0 +1,788 @@
+// C ABI of the bsreg Gibbs hot path (see include/bsreg_cuda.h for the mapping to the
+// reference's R6 protocol).  Host-side orchestration only: device memory, streams,
+// CUDA graphs, chain sharding over GPUs.  No CPU fallback: without a usable CUDA
+// device every entry point fails with BSREG_ENOGPU / BSREG_ECUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bsreg_cuda.h"
+#include "internal.cuh"
+
+using namespace bsreg;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(e_ == cudaErrorMemoryAllocation ? BSREG_ENOMEM : BSREG_ECUDA, "%s: %s (%s:%d)",  \
+                  #expr, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int r_ = (expr);         \
+    if (r_ != BSREG_OK) return r_; \
+  } while (0)
+
+constexpr int GRAPH_UNROLL = 20;      // Gibbs iterations per CUDA graph launch
+constexpr int BLOCK_ITERS = 1000;     // iterations between host syncs / progress callbacks
+constexpr size_t DRAW_BUF_BYTES = (size_t)1 << 30;
+
+struct Shard {
+  int dev = 0, sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int chain_lo = 0;                   // first chain of this shard inside the handle
+  DeviceData dd{};
+  ChainState cs{};
+  std::vector<void *> allocs;
+  RunCtl *ctl_dev = nullptr;
+  double *draws_dev = nullptr;
+  int save_cap = 0;
+  double *p0_init = nullptr, *beta0 = nullptr;
+  double *scratch = nullptr;          // partial sums for deterministic reductions
+  cudaGraphExec_t graph = nullptr;
+
+  template <class T>
+  int alloc(T **p, size_t count) {
+    void *q = nullptr;
+    CU(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    allocs.push_back(q);
+    *p = static_cast<T *>(q);
+    return BSREG_OK;
+  }
+};
+
+}  // namespace
+
+struct bsreg_handle {
+  int n = 0, k = 0, m = 0, d = 0, P = 0, model = 0, prior = 0, ldet = 0, stats_mode = 0, n_chains = 0;
+  bool spatial = false;
+  Priors pr{};
+  bsreg_options opt{};
+  std::vector<Shard> shards;
+  int64_t launches = 0;
+  int64_t nnz = 0;
+  std::vector<double> node_re, node_im, node_w;
+};
+
+namespace {
+
+int upload(Shard &s, const void *src, void *dst, size_t bytes) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s.stream));
+  return BSREG_OK;
+}
+
+// one Gibbs iteration = [fused sweep] + chain step
+int enqueue_iteration(bsreg_handle *h, Shard &s) {
+  if (h->stats_mode == BSREG_STATS_STREAM) { launch_sweep(s.dd, s.sm_count, s.stream); ++h->launches; }
+  launch_chain_step(s.dd, h->pr, s.cs, s.ctl_dev, s.draws_dev, s.stream);
+  ++h->launches;
+  return BSREG_OK;
+}
+
+int build_graph(bsreg_handle *h, Shard &s) {
+  if (s.graph) return BSREG_OK;
+  cudaGraph_t g = nullptr;
+  CU(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+  const int64_t before = h->launches;
+  for (int i = 0; i < GRAPH_UNROLL; ++i) enqueue_iteration(h, s);
+  h->launches = before;
+  CU(cudaStreamEndCapture(s.stream, &g));
+  CU(cudaGraphInstantiate(&s.graph, g, 0));
+  CU(cudaGraphDestroy(g));
+  return BSREG_OK;
+}
+
+int enqueue_iterations(bsreg_handle *h, Shard &s, int count) {
+  const int per_iter = h->stats_mode == BSREG_STATS_STREAM ? 2 : 1;
+  if (count >= GRAPH_UNROLL) TRY(build_graph(h, s));
+  while (count >= GRAPH_UNROLL) {
+    CU(cudaGraphLaunch(s.graph, s.stream));
+    h->launches += (int64_t)GRAPH_UNROLL * per_iter;
+    count -= GRAPH_UNROLL;
+  }
+  for (; count > 0; --count) enqueue_iteration(h, s);
+  CU(cudaGetLastError());
+  return BSREG_OK;
+}
+
+// tr(W^2) = sum_ij W_ij W_ji, exact from CSR (host, setup only)
+double trace_w2(int n, const int32_t *rp, const int32_t *ci, const double *va) {
+  long double acc = 0.0L;
+  for (int i = 0; i < n; ++i)
+    for (int p = rp[i]; p < rp[i + 1]; ++p) {
+      const int j = ci[p];
+      for (int q = rp[j]; q < rp[j + 1]; ++q)
+        if (ci[q] == i) acc += (long double)va[p] * va[q];
+    }
+  return (double)acc;
+}
+
+int trace_moments_dev(bsreg_handle *h, Shard &s, const bsreg_problem *prob_csr, int order, int probes, uint64_t seed,
+                      double *moments) {
+  const int n = h->n;
+  for (int j = 0; j <= order; ++j) moments[j] = 0.0;
+  moments[0] = n;
+  if (order >= 1) {
+    long double tr = 0.0L;
+    for (int i = 0; i < n; ++i)
+      for (int p = prob_csr->row_ptr[i]; p < prob_csr->row_ptr[i + 1]; ++p)
+        if (prob_csr->col_idx[p] == i) tr += prob_csr->val[p];
+    moments[1] = (double)tr;
+  }
+  if (order >= 2) moments[2] = 2.0 * trace_w2(n, prob_csr->row_ptr, prob_csr->col_idx, prob_csr->val) - n;
+  if (order < 3) return BSREG_OK;
+  CU(cudaSetDevice(s.dev));
+  const size_t len = (size_t)n * probes;
+  double *U = nullptr, *buf[3] = {nullptr, nullptr, nullptr}, *res = nullptr;
+  CU(cudaMalloc(&U, len * 8));
+  for (int b = 0; b < 3; ++b) CU(cudaMalloc(&buf[b], len * 8));
+  CU(cudaMalloc(&res, (order + 1) * 8));
+  launch_probes(U, n, probes, seed, s.stream);
+  // T_1 = W U ; T_j = 2 W T_{j-1} - T_{j-2}; U stays intact for the dots u'T_j u
+  launch_spmm(n, s.dd.rp, s.dd.ci, s.dd.va, U, probes, probes, buf[0], probes, 0, 1.0, nullptr, 0.0, s.stream);
+  h->launches += 2;
+  const double *prev = U;
+  double *cur = buf[0];
+  int nxt = 1;
+  for (int j = 2; j <= order; ++j) {
+    double *next = buf[nxt];
+    launch_spmm(n, s.dd.rp, s.dd.ci, s.dd.va, cur, probes, probes, next, probes, 0, 2.0, prev, -1.0, s.stream);
+    ++h->launches;
+    if (j >= 3) { launch_dot(U, next, (int64_t)len, s.scratch, res + j, s.stream); h->launches += 2; }
+    prev = cur; cur = next; nxt = (nxt + 1) % 3;
+  }
+  std::vector<double> host(order + 1);
+  CU(cudaMemcpyAsync(host.data(), res, (order + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
+  CU(cudaStreamSynchronize(s.stream));
+  for (int j = 3; j <= order; ++j) moments[j] = host[j] / probes;
+  cudaFree(U); cudaFree(buf[0]); cudaFree(buf[1]); cudaFree(buf[2]); cudaFree(res);
+  return BSREG_OK;
+}
+
+void chebyshev_nodes(const std::vector<double> &mom, int n, std::vector<double> &re, std::vector<double> &im,
+                     std::vector<double> &w) {
+  const int q = (int)mom.size() - 1;
+  re.assign(q + 1, 0.0); im.assign(q + 1, 0.0); w.assign(q + 1, 0.0);
+  for (int k = 1; k <= q + 1; ++k) {
+    const double theta = M_PI * (k - 0.5) / (q + 1);
+    double acc = 0.5 * n;
+    for (int j = 1; j <= q; ++j) acc += mom[j] * std::cos(theta * j);
+    re[k - 1] = std::cos(theta);
+    w[k - 1] = 2.0 / (q + 1) * acc;
+  }
+}
+
+int set_nodes(bsreg_handle *h) {
+  for (Shard &s : h->shards) {
+    CU(cudaSetDevice(s.dev));
+    const int nn = (int)h->node_re.size();
+    double *re, *im, *w;
+    TRY(s.alloc(&re, nn)); TRY(s.alloc(&im, nn)); TRY(s.alloc(&w, nn));
+    TRY(upload(s, h->node_re.data(), re, nn * 8));
+    TRY(upload(s, h->node_im.data(), im, nn * 8));
+    TRY(upload(s, h->node_w.data(), w, nn * 8));
+    s.dd.n_nodes = nn; s.dd.node_re = re; s.dd.node_im = im; s.dd.node_w = w;
+  }
+  return BSREG_OK;
+}
+
+int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_options *o, int n_chains, int chain_lo) {
+  CU(cudaSetDevice(s.dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, s.dev));
+  s.sm_count = prop.multiProcessorCount;
+  if (o->stream && h->shards.size() == 1) { s.stream = (cudaStream_t)o->stream; s.own_stream = false; }
+  else { CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)); s.own_stream = true; }
+  s.chain_lo = chain_lo;
+  const int n = h->n, k = h->k, m = h->m, d = h->d;
+  DeviceData &dd = s.dd;
+  dd.n = n; dd.m = m; dd.d = d; dd.model = h->model; dd.nnz = p->nnz;
+
+  // ---- W (CSR) ----
+  int *rp = nullptr, *ci = nullptr; double *va = nullptr;
+  if (p->nnz > 0 || h->model != BSREG_MODEL_LM || p->k_slx > 0) {
+    TRY(s.alloc(&rp, (size_t)n + 1)); TRY(s.alloc(&ci, (size_t)p->nnz)); TRY(s.alloc(&va, (size_t)p->nnz));
+    TRY(upload(s, p->row_ptr, rp, ((size_t)n + 1) * 4));
+    TRY(upload(s, p->col_idx, ci, (size_t)p->nnz * 4));
+    TRY(upload(s, p->val, va, (size_t)p->nnz * 8));
+  }
+  dd.rp = rp; dd.ci = ci; dd.va = va;
+
+  // ---- y, X (column-major on the host -> row-major [n][m] in HBM) ----
+  double *y, *X, *tmp;
+  TRY(s.alloc(&y, (size_t)n)); TRY(s.alloc(&X, (size_t)n * m));
+  CU(cudaMalloc(&tmp, (size_t)n * std::max(k, std::max(p->k_slx, 1)) * 8));
+  TRY(upload(s, p->y, y, (size_t)n * 8));
+  TRY(upload(s, p->X, tmp, (size_t)n * k * 8));
+  launch_transpose(tmp, X, n, k, m, 0, s.stream);
+  if (p->k_slx > 0) {   // setup_2SLX fixed-W branch, R/12_slx.R:60-68: X <- [X, Psi_SLX %*% X_SLX]
+    double *xs_rm; int *rps = rp, *cis = ci; double *vas = va;
+    CU(cudaStreamSynchronize(s.stream));
+    TRY(upload(s, p->X_slx, tmp, (size_t)n * p->k_slx * 8));
+    CU(cudaMalloc(&xs_rm, (size_t)n * p->k_slx * 8));
+    launch_transpose(tmp, xs_rm, n, p->k_slx, p->k_slx, 0, s.stream);
+    if (p->nnz_slx > 0) {
+      CU(cudaMalloc(&rps, ((size_t)n + 1) * 4)); CU(cudaMalloc(&cis, (size_t)p->nnz_slx * 4)); CU(cudaMalloc(&vas, (size_t)p->nnz_slx * 8));
+      TRY(upload(s, p->row_ptr_slx, rps, ((size_t)n + 1) * 4));
+      TRY(upload(s, p->col_idx_slx, cis, (size_t)p->nnz_slx * 4));
+      TRY(upload(s, p->val_slx, vas, (size_t)p->nnz_slx * 8));
+    }
+    launch_spmm(n, rps, cis, vas, xs_rm, p->k_slx, p->k_slx, X, m, k, 1.0, nullptr, 0.0, s.stream);
+    CU(cudaStreamSynchronize(s.stream));
+    cudaFree(xs_rm);
+    if (p->nnz_slx > 0) { cudaFree(rps); cudaFree(cis); cudaFree(vas); }
+    h->launches += 2;
+  }
+  CU(cudaStreamSynchronize(s.stream));
+  cudaFree(tmp);
+  dd.y = y; dd.X = X;
+  h->launches += 1;
+
+  // ---- cached lags (R/15_sar.R:57, R/15_sem.R:63-64) ----
+  dd.Wy = nullptr; dd.WX = nullptr;
+  if (h->model != BSREG_MODEL_LM) {
+    TRY(s.alloc(&dd.Wy, (size_t)n));
+    launch_spmm(n, rp, ci, va, y, 1, 1, dd.Wy, 1, 0, 1.0, nullptr, 0.0, s.stream);
+    ++h->launches;
+  }
+  if (h->model == BSREG_MODEL_SEM) {
+    TRY(s.alloc(&dd.WX, (size_t)n * m));
+    launch_spmm(n, rp, ci, va, X, m, m, dd.WX, m, 0, 1.0, nullptr, 0.0, s.stream);
+    ++h->launches;
+  }
+
+  // ---- Gram accumulators and fixed-point scales ----
+  double *norms, *gscale, *ginv;
+  TRY(s.alloc(&dd.G, (size_t)d * d)); TRY(s.alloc(&dd.Gfix, (size_t)d * d)); TRY(s.alloc(&dd.ticket, 1));
+  TRY(s.alloc(&norms, (size_t)d)); TRY(s.alloc(&gscale, (size_t)d * d)); TRY(s.alloc(&ginv, (size_t)d * d));
+  TRY(s.alloc(&s.scratch, 4096));
+  CU(cudaMemsetAsync(dd.Gfix, 0, (size_t)d * d * 8, s.stream));
+  CU(cudaMemsetAsync(dd.ticket, 0, 4, s.stream));
+  launch_colnorms(dd, norms, s.stream);
+  ++h->launches;
+  std::vector<double> hn(d), hs((size_t)d * d), hi((size_t)d * d);
+  CU(cudaMemcpyAsync(hn.data(), norms, (size_t)d * 8, cudaMemcpyDeviceToHost, s.stream));
+  CU(cudaStreamSynchronize(s.stream));
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) {
+      const double bound = std::sqrt(hn[i] * hn[j]);
+      int e = 0;
+      if (bound > 0.0 && std::isfinite(bound)) e = std::ilogb(bound) + 1;
+      hs[(size_t)i * d + j] = std::ldexp(1.0, e - 61);
+      hi[(size_t)i * d + j] = std::ldexp(1.0, 61 - e);
+    }
+  TRY(upload(s, hs.data(), gscale, (size_t)d * d * 8));
+  TRY(upload(s, hi.data(), ginv, (size_t)d * d * 8));
+  CU(cudaStreamSynchronize(s.stream));
+  dd.Gscale = gscale; dd.Ginv_scale = ginv;
+  launch_sweep(dd, s.sm_count, s.stream);
+  ++h->launches;
+
+  // ---- chain state ----
+  ChainState &cs = s.cs;
+  cs.n_chains = n_chains; cs.chain_offset = o->chain_offset + chain_lo; cs.seed = o->seed;
+  const int A = aux_len(m);
+  double *mu0;
+  TRY(s.alloc(&cs.beta, (size_t)n_chains * m)); TRY(s.alloc(&cs.sigma2, (size_t)n_chains)); TRY(s.alloc(&cs.lam, (size_t)n_chains));
+  TRY(s.alloc(&cs.p0, (size_t)n_chains * m)); TRY(s.alloc(&cs.aux, (size_t)n_chains * A));
+  TRY(s.alloc(&cs.mh_scale, (size_t)n_chains * 2)); TRY(s.alloc(&cs.mh_cnt, (size_t)n_chains * 8));
+  TRY(s.alloc(&cs.iters, (size_t)n_chains)); TRY(s.alloc(&cs.step, (size_t)n_chains));
+  TRY(s.alloc(&mu0, (size_t)m)); TRY(s.alloc(&s.p0_init, (size_t)m)); TRY(s.alloc(&s.ctl_dev, 1));
+  CU(cudaMemsetAsync(cs.aux, 0, (size_t)n_chains * A * 8, s.stream));
+  CU(cudaMemsetAsync(cs.step, 0, (size_t)n_chains * 4, s.stream));
+  std::vector<double> hmu(m), hp0(m);
+  for (int a = 0; a < m; ++a) {
+    hmu[a] = o->ng_mu ? o->ng_mu[o->ng_mu_len == 1 ? 0 : a] : 0.0;
+    hp0[a] = o->ng_precision ? o->ng_precision[o->ng_precision_len == 1 ? 0 : a] : 1e-8;
+  }
+  TRY(upload(s, hmu.data(), mu0, (size_t)m * 8));
+  TRY(upload(s, hp0.data(), s.p0_init, (size_t)m * 8));
+  if (o->ng_beta0) { TRY(s.alloc(&s.beta0, (size_t)m)); TRY(upload(s, o->ng_beta0, s.beta0, (size_t)m * 8)); }
+  CU(cudaStreamSynchronize(s.stream));
+  cs.mu0 = mu0;
+  return BSREG_OK;
+}
+
+int init_chains(bsreg_handle *h, bool refresh_only) {
+  const bsreg_options &o = h->opt;
+  for (Shard &s : h->shards) {
+    CU(cudaSetDevice(s.dev));
+    ChainInit ci{s.beta0, o.ng_sigma0, o.sp_lambda, o.sp_lambda_scale, o.hs_lambda, o.hs_tau, o.hs_zeta, o.hs_nu,
+                 o.sng_lambda, o.sng_tau, o.sng_theta, o.sng_theta_scale, s.p0_init, refresh_only};
+    launch_chain_init(s.dd, h->pr, s.cs, ci, s.stream);
+    ++h->launches;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s.stream));
+  }
+  return BSREG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bsreg_abi_version(void) { return BSREG_ABI_VERSION; }
+const char *bsreg_last_error(void) { return g_err.c_str(); }
+
+int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **out) {
+  if (!p || !o || !out) return fail(BSREG_EINVAL, "null argument");
+  *out = nullptr;
+  if (p->n <= 0 || p->k <= 0 || !p->y || !p->X) return fail(BSREG_EINVAL, "need n > 0, k > 0, y and X");
+  if (o->model < 0 || o->model > 2 || o->prior < 0 || o->prior > 3) return fail(BSREG_EINVAL, "bad model or prior code");
+  if (o->n_chains <= 0) return fail(BSREG_EINVAL, "n_chains must be positive");
+  const bool need_w = o->model != BSREG_MODEL_LM || p->k_slx > 0;
+  if (need_w && (!p->row_ptr || !p->col_idx || !p->val || p->nnz <= 0))
+    return fail(BSREG_EINVAL, "Please provide a connectivity matrix (CSR row_ptr/col_idx/val)");   // R/15_sar.R:52
+  if (need_w) {
+    if (p->row_ptr[0] != 0 || p->row_ptr[p->n] != p->nnz) return fail(BSREG_EINVAL, "CSR row_ptr inconsistent with nnz");
+    for (int64_t q = 0; q < p->nnz; ++q)
+      if (p->col_idx[q] < 0 || p->col_idx[q] >= p->n) return fail(BSREG_EINVAL, "CSR column index out of range");
+  }
+  if (p->k_slx > 0 && !p->X_slx) return fail(BSREG_EINVAL, "k_slx > 0 needs X_slx");
+  int ndev_avail = 0;
+  if (cudaGetDeviceCount(&ndev_avail) != cudaSuccess || ndev_avail == 0) {
+    cudaGetLastError();
+    return fail(BSREG_ENOGPU, "no CUDA device available (this library has no CPU fallback)");
+  }
+
+  bsreg_handle *h = new bsreg_handle();
+  h->n = p->n; h->k = p->k; h->m = p->k + p->k_slx; h->model = o->model; h->prior = o->prior;
+  h->ldet = o->ldet; h->stats_mode = o->stats_mode; h->n_chains = o->n_chains; h->opt = *o; h->nnz = p->nnz;
+  h->spatial = o->model != BSREG_MODEL_LM;
+  h->d = (o->model == BSREG_MODEL_SEM) ? 2 * h->m + 2 : h->m + 2;
+  h->P = h->m + 1 + (h->spatial ? 1 : 0);
+  if (h->n <= h->m) { delete h; return fail(BSREG_EINVAL, "need n > number of regressors"); }
+  if (chain_smem_bytes(h->m, h->model, h->prior) > 227 * 1024) {
+    delete h;
+    return fail(BSREG_EINVAL, "too many regressors for the on-chip chain step (M = %d)", h->m);
+  }
+  if (h->spatial && o->ldet == BSREG_LDET_NONE) { delete h; return fail(BSREG_EINVAL, "spatial model needs a log-determinant method"); }
+  if (h->spatial && o->ldet == BSREG_LDET_NODES && (p->n_nodes <= 0 || !p->node_re || !p->node_w)) {
+    delete h; return fail(BSREG_EINVAL, "BSREG_LDET_NODES needs node_re / node_w");
+  }
+
+  Priors &pr = h->pr;
+  pr.prior = o->prior;
+  pr.shape0 = o->ng_shape; pr.rate0 = o->ng_rate; pr.shape1 = o->ng_shape + 0.5 * (double)p->n;   // R/10_lm.R:152
+  pr.sng_lambda_a = o->sng_lambda_a; pr.sng_lambda_b = o->sng_lambda_b;
+  pr.sng_theta_scale = o->sng_theta_scale; pr.sng_theta_a = o->sng_theta_a;
+  pr.lam_a = o->sp_lambda_a; pr.lam_b = o->sp_lambda_b; pr.lam_lo = o->sp_lambda_min; pr.lam_hi = o->sp_lambda_max;
+  pr.lbeta_ab = std::lgamma(pr.lam_a) + std::lgamma(pr.lam_b) - std::lgamma(pr.lam_a + pr.lam_b);
+  // the copied options must not keep dangling host pointers
+  h->opt.ng_mu = nullptr; h->opt.ng_precision = nullptr; h->opt.ng_beta0 = nullptr; h->opt.devices = nullptr; h->opt.stream = nullptr;
+
+  int cur = 0;
+  cudaGetDevice(&cur);
+  const int ndev = o->n_devices > 0 ? o->n_devices : 1;
+  if (ndev > o->n_chains) { delete h; return fail(BSREG_EINVAL, "more devices than chains"); }
+  h->shards.resize(ndev);
+  int rc = BSREG_OK, lo = 0;
+  for (int g = 0; g < ndev && rc == BSREG_OK; ++g) {
+    Shard &s = h->shards[g];
+    s.dev = o->n_devices > 0 && o->devices ? o->devices[g] : cur;
+    if (s.dev < 0 || s.dev >= ndev_avail) { rc = fail(BSREG_EINVAL, "device %d not available", s.dev); break; }
+    const int cnt = o->n_chains / ndev + (g < o->n_chains % ndev ? 1 : 0);   // contiguous blocks of chain ids
+    rc = setup_shard(h, s, p, o, cnt, lo);
+    lo += cnt;
+  }
+  // ---- log-determinant nodes ----
+  if (rc == BSREG_OK && h->spatial) {
+    if (o->ldet == BSREG_LDET_NODES) {
+      h->node_re.assign(p->node_re, p->node_re + p->n_nodes);
+      if (p->node_im) h->node_im.assign(p->node_im, p->node_im + p->n_nodes); else h->node_im.assign(p->n_nodes, 0.0);
+      h->node_w.assign(p->node_w, p->node_w + p->n_nodes);
+    } else {
+      const int order = o->cheb_order > 0 ? o->cheb_order : 50, probes = o->cheb_probes > 0 ? o->cheb_probes : 64;
+      std::vector<double> mom(order + 1);
+      rc = trace_moments_dev(h, h->shards[0], p, order, probes, o->seed, mom.data());
+      if (rc == BSREG_OK) chebyshev_nodes(mom, h->n, h->node_re, h->node_im, h->node_w);
+    }
+    if (rc == BSREG_OK) rc = set_nodes(h);
+  }
+  if (rc == BSREG_OK) rc = init_chains(h, false);
+  cudaSetDevice(cur);
+  if (rc != BSREG_OK) { std::string keep = g_err; bsreg_destroy(h); g_err = keep; return rc; }
+  *out = h;
+  return BSREG_OK;
+}
+
+void bsreg_destroy(bsreg_handle *h) {
+  if (!h) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (Shard &s : h->shards) {
+    cudaSetDevice(s.dev);
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.graph) cudaGraphExecDestroy(s.graph);
+    for (void *q : s.allocs) cudaFree(q);
+    if (s.draws_dev) cudaFree(s.draws_dev);
+    if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
+  }
+  cudaSetDevice(cur);
+  delete h;
+}
+
+int bsreg_dims(const bsreg_handle *h, int32_t *n, int32_t *m, int32_t *p, int32_t *n_chains, int32_t *d) {
+  if (!h) return fail(BSREG_EINVAL, "null handle");
+  if (n) *n = h->n;
+  if (m) *m = h->m;
+  if (p) *p = h->P;
+  if (n_chains) *n_chains = h->n_chains;
+  if (d) *d = h->d;
+  return BSREG_OK;
+}
+
+int bsreg_run(bsreg_handle *h, int32_t n_burn, int32_t n_save, const bsreg_mh *mh, double *draws,
+              bsreg_progress_fn progress, void *user) {
+  if (!h) return fail(BSREG_EINVAL, "null handle");
+  if (n_burn < 0 || n_save < 0) return fail(BSREG_EINVAL, "n_burn and n_save must be non-negative");
+  const bsreg_mh def{0.8, 0.20, 0.45, 0.8};
+  if (!mh) mh = &def;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  const int64_t total = (int64_t)n_burn + n_save;
+  // draw buffers
+  for (Shard &s : h->shards) {
+    CU(cudaSetDevice(s.dev));
+    const size_t row_bytes = (size_t)h->P * s.cs.n_chains * 8;
+    int cap = (int)std::min<size_t>((size_t)std::max(n_save, 1), std::max<size_t>(DRAW_BUF_BYTES / row_bytes, 1));
+    if (cap > s.save_cap) {
+      CU(cudaStreamSynchronize(s.stream));
+      if (s.graph) { cudaGraphExecDestroy(s.graph); s.graph = nullptr; }   // the graph bakes the buffer pointer
+      if (s.draws_dev) cudaFree(s.draws_dev);
+      s.draws_dev = nullptr;
+      CU(cudaMalloc(&s.draws_dev, (size_t)cap * row_bytes));
+      s.save_cap = cap;
+    }
+    CU(cudaMemsetAsync(s.cs.step, 0, (size_t)s.cs.n_chains * 4, s.stream));
+  }
+  RunCtl ctl{};
+  ctl.n_burn = n_burn; ctl.n_save = n_save;
+  ctl.tune_limit = (int)std::floor(mh->adjust_burn * (double)n_burn);   // i <= adjust_burn * n_burn, R/50_execute.R:62
+  ctl.acc_lo = mh->acc_lo; ctl.acc_hi = mh->acc_hi; ctl.acc_change = mh->acc_change;
+  ctl.store = 1;
+  int64_t done = 0;
+  int rc = BSREG_OK;
+  while (done < total && rc == BSREG_OK) {
+    int nb;
+    const bool saving = done >= n_burn;
+    if (!saving) nb = (int)std::min<int64_t>(BLOCK_ITERS, n_burn - done);
+    else nb = (int)std::min<int64_t>(BLOCK_ITERS, total - done);
+    for (Shard &s : h->shards) {
+      CU(cudaSetDevice(s.dev));
+      int nbs = nb;
+      if (saving) nbs = std::min(nbs, s.save_cap);
+      nb = std::min(nb, nbs);
+    }
+    for (Shard &s : h->shards) {
+      CU(cudaSetDevice(s.dev));
+      ctl.save_cap = s.save_cap;
+      ctl.save_base = saving ? (int)(done - n_burn) : 0;
+      CU(cudaMemcpyAsync(s.ctl_dev, &ctl, sizeof ctl, cudaMemcpyHostToDevice, s.stream));
+      TRY(enqueue_iterations(h, s, nb));
+      if (saving && draws) {
+        double *dst = draws + (size_t)s.chain_lo * h->P * n_save + ctl.save_base;
+        CU(cudaMemcpy2DAsync(dst, (size_t)n_save * 8, s.draws_dev, (size_t)s.save_cap * 8, (size_t)nb * 8,
+                             (size_t)h->P * s.cs.n_chains, cudaMemcpyDeviceToHost, s.stream));
+      }
+    }
+    for (Shard &s : h->shards) {
+      CU(cudaSetDevice(s.dev));
+      CU(cudaStreamSynchronize(s.stream));
+    }
+    done += nb;
+    if (progress && progress(done, total, user) != 0) rc = fail(BSREG_EABORT, "aborted by progress callback");
+  }
+  cudaSetDevice(cur);
+  return rc;
+}
+
+int bsreg_fetch_draws(bsreg_handle *h, int32_t first, int32_t count, double *draws) {
+  if (!h || !draws) return fail(BSREG_EINVAL, "null argument");
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (Shard &s : h->shards) {
+    if (first < 0 || count < 0 || first + count > s.save_cap) return fail(BSREG_EINVAL, "rows outside the device draw buffer");
+    CU(cudaSetDevice(s.dev));
+    double *dst = draws + (size_t)s.chain_lo * h->P * count;
+    CU(cudaMemcpy2DAsync(dst, (size_t)count * 8, s.draws_dev + first, (size_t)s.save_cap * 8, (size_t)count * 8,
+                         (size_t)h->P * s.cs.n_chains, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+  }
+  cudaSetDevice(cur);
+  return BSREG_OK;
+}
+
+int bsreg_aux_len(const bsreg_handle *h) { return h ? aux_len(h->m) : 0; }
+
+int bsreg_get_state(bsreg_handle *h, double *params, double *p0, double *aux, double *mh_value, double *mh_scale,
+                    int64_t *mh_counters, int64_t *iterations) {
+  if (!h) return fail(BSREG_EINVAL, "null handle");
+  int cur = 0;
+  cudaGetDevice(&cur);
+  const int m = h->m, P = h->P, A = aux_len(m);
+  for (Shard &s : h->shards) {
+    CU(cudaSetDevice(s.dev));
+    const int C = s.cs.n_chains, lo = s.chain_lo;
+    std::vector<double> beta((size_t)C * m), s2(C), lam(C), ax((size_t)C * A), sc((size_t)C * 2);
+    CU(cudaMemcpy(beta.data(), s.cs.beta, beta.size() * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(s2.data(), s.cs.sigma2, (size_t)C * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(lam.data(), s.cs.lam, (size_t)C * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ax.data(), s.cs.aux, ax.size() * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(sc.data(), s.cs.mh_scale, sc.size() * 8, cudaMemcpyDeviceToHost));
+    for (int c = 0; c < C; ++c) {
+      if (params) {
+        double *dst = params + (size_t)(lo + c) * P;
+        std::copy(beta.begin() + (size_t)c * m, beta.begin() + (size_t)(c + 1) * m, dst);
+        dst[m] = s2[c];
+        if (h->spatial) dst[m + 1] = lam[c];
+      }
+      if (aux) std::copy(ax.begin() + (size_t)c * A, ax.begin() + (size_t)(c + 1) * A, aux + (size_t)(lo + c) * A);
+      if (mh_value) { mh_value[2 * (lo + c)] = lam[c]; mh_value[2 * (lo + c) + 1] = ax[(size_t)c * A + 2 * m + 1]; }
+      if (mh_scale) { mh_scale[2 * (lo + c)] = sc[2 * c]; mh_scale[2 * (lo + c) + 1] = sc[2 * c + 1]; }
+    }
+    if (p0) CU(cudaMemcpy(p0 + (size_t)lo * m, s.cs.p0, (size_t)C * m * 8, cudaMemcpyDeviceToHost));
+    if (mh_counters) CU(cudaMemcpy(mh_counters + (size_t)lo * 8, s.cs.mh_cnt, (size_t)C * 8 * 8, cudaMemcpyDeviceToHost));
+    if (iterations) CU(cudaMemcpy(iterations + lo, s.cs.iters, (size_t)C * 8, cudaMemcpyDeviceToHost));
+  }
+  cudaSetDevice(cur);
+  return BSREG_OK;
+}
+
+int bsreg_set_state(bsreg_handle *h, const double *params, const double *p0, const double *aux, const double *mh_value,
+                    const double *mh_scale, const int64_t *mh_counters, const int64_t *iterations) {
+  if (!h) return fail(BSREG_EINVAL, "null handle");
+  (void)mh_value;   // the MH values are the parameters themselves (lambda in params, theta in aux)
+  int cur = 0;
+  cudaGetDevice(&cur);
+  const int m = h->m, P = h->P, A = aux_len(m);
+  for (Shard &s : h->shards) {
+    CU(cudaSetDevice(s.dev));
+    CU(cudaStreamSynchronize(s.stream));
+    const int C = s.cs.n_chains, lo = s.chain_lo;
+    if (params) {
+      std::vector<double> beta((size_t)C * m), s2(C), lam(C, 0.0);
+      for (int c = 0; c < C; ++c) {
+        const double *src = params + (size_t)(lo + c) * P;
+        std::copy(src, src + m, beta.begin() + (size_t)c * m);
+        s2[c] = src[m];
+        if (h->spatial) lam[c] = src[m + 1];
+      }
+      CU(cudaMemcpy(s.cs.beta, beta.data(), beta.size() * 8, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(s.cs.sigma2, s2.data(), (size_t)C * 8, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(s.cs.lam, lam.data(), (size_t)C * 8, cudaMemcpyHostToDevice));
+    }
+    if (p0) CU(cudaMemcpy(s.cs.p0, p0 + (size_t)lo * m, (size_t)C * m * 8, cudaMemcpyHostToDevice));
+    if (aux) CU(cudaMemcpy(s.cs.aux, aux + (size_t)lo * A, (size_t)C * A * 8, cudaMemcpyHostToDevice));
+    if (mh_scale) CU(cudaMemcpy(s.cs.mh_scale, mh_scale + (size_t)lo * 2, (size_t)C * 2 * 8, cudaMemcpyHostToDevice));
+    if (mh_counters) CU(cudaMemcpy(s.cs.mh_cnt, mh_counters + (size_t)lo * 8, (size_t)C * 8 * 8, cudaMemcpyHostToDevice));
+    if (iterations) CU(cudaMemcpy(s.cs.iters, iterations + lo, (size_t)C * 8, cudaMemcpyHostToDevice));
+  }
+  cudaSetDevice(cur);
+  return init_chains(h, true);    // recompute the cached log-det / rss at the restored lambda
+}
+
+// ---- parity entry points (shard 0) ----
+int bsreg_eval_spmm(bsreg_handle *h, const double *B, int32_t mcols, double *out) {
+  if (!h || !B || !out || mcols <= 0) return fail(BSREG_EINVAL, "bad argument");
+  Shard &s = h->shards[0];
+  if (!s.dd.rp) return fail(BSREG_EINVAL, "handle has no W");
+  CU(cudaSetDevice(s.dev));
+  const size_t len = (size_t)h->n * mcols;
+  double *cm, *rm, *orm;
+  CU(cudaMalloc(&cm, len * 8)); CU(cudaMalloc(&rm, len * 8)); CU(cudaMalloc(&orm, len * 8));
+  CU(cudaMemcpyAsync(cm, B, len * 8, cudaMemcpyHostToDevice, s.stream));
+  launch_transpose(cm, rm, h->n, mcols, mcols, 0, s.stream);
+  launch_spmm(h->n, s.dd.rp, s.dd.ci, s.dd.va, rm, mcols, mcols, orm, mcols, 0, 1.0, nullptr, 0.0, s.stream);
+  h->launches += 2;
+  std::vector<double> host(len);
+  CU(cudaMemcpyAsync(host.data(), orm, len * 8, cudaMemcpyDeviceToHost, s.stream));
+  CU(cudaStreamSynchronize(s.stream));
+  for (int i = 0; i < h->n; ++i)
+    for (int c = 0; c < mcols; ++c) out[(size_t)c * h->n + i] = host[(size_t)i * mcols + c];
+  cudaFree(cm); cudaFree(rm); cudaFree(orm);
+  return BSREG_OK;
+}
+
+int bsreg_eval_gram(bsreg_handle *h, double *G) {
+  if (!h || !G) return fail(BSREG_EINVAL, "bad argument");
+  Shard &s = h->shards[0];
+  CU(cudaSetDevice(s.dev));
+  launch_sweep(s.dd, s.sm_count, s.stream);
+  ++h->launches;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(G, s.dd.G, (size_t)h->d * h->d * 8, cudaMemcpyDeviceToHost, s.stream));
+  CU(cudaStreamSynchronize(s.stream));
+  return BSREG_OK;
+}
+
+int bsreg_eval_residual_ss(bsreg_handle *h, int32_t n_eval, const double *beta, const double *lam, const double *rho,
+                           double *ss) {
+  if (!h || !beta || !lam || !rho || !ss || n_eval <= 0) return fail(BSREG_EINVAL, "bad argument");
+  Shard &s = h->shards[0];
+  CU(cudaSetDevice(s.dev));
+  double *db, *dl, *dr, *dout, *part;
+  CU(cudaMalloc(&db, (size_t)n_eval * h->m * 8)); CU(cudaMalloc(&dl, (size_t)n_eval * 8)); CU(cudaMalloc(&dr, (size_t)n_eval * 8));
+  CU(cudaMalloc(&dout, (size_t)n_eval * 8)); CU(cudaMalloc(&part, (size_t)592 * 4 * 8));
+  CU(cudaMemcpyAsync(db, beta, (size_t)n_eval * h->m * 8, cudaMemcpyHostToDevice, s.stream));
+  CU(cudaMemcpyAsync(dl, lam, (size_t)n_eval * 8, cudaMemcpyHostToDevice, s.stream));
+  CU(cudaMemcpyAsync(dr, rho, (size_t)n_eval * 8, cudaMemcpyHostToDevice, s.stream));
+  launch_residual_ss(s.dd, n_eval, db, dl, dr, part, dout, s.stream);
+  h->launches += 2 * ((n_eval + 3) / 4);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ss, dout, (size_t)n_eval * 8, cudaMemcpyDeviceToHost, s.stream));
+  CU(cudaStreamSynchronize(s.stream));
+  cudaFree(db); cudaFree(dl); cudaFree(dr); cudaFree(dout); cudaFree(part);
+  return BSREG_OK;
+}
+
+int bsreg_eval_logdet(bsreg_handle *h, int32_t n_eval, const double *v, double *ldet) {
+  if (!h || !v || !ldet || n_eval <= 0) return fail(BSREG_EINVAL, "bad argument");
+  Shard &s = h->shards[0];
+  if (s.dd.n_nodes <= 0) return fail(BSREG_EINVAL, "handle has no log-determinant nodes");
+  CU(cudaSetDevice(s.dev));
+  double *dv, *dout;
+  CU(cudaMalloc(&dv, (size_t)n_eval * 8)); CU(cudaMalloc(&dout, (size_t)n_eval * 8));
+  CU(cudaMemcpyAsync(dv, v, (size_t)n_eval * 8, cudaMemcpyHostToDevice, s.stream));
+  launch_eval_logdet(s.dd, n_eval, dv, dout, s.stream);
+  ++h->launches;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ldet, dout, (size_t)n_eval * 8, cudaMemcpyDeviceToHost, s.stream));
+  CU(cudaStreamSynchronize(s.stream));
+  cudaFree(dv); cudaFree(dout);
+  return BSREG_OK;
+}
+
+int bsreg_n_nodes(const bsreg_handle *h) { return h ? (int)h->node_re.size() : 0; }
+
+int bsreg_get_nodes(bsreg_handle *h, double *re, double *im, double *w) {
+  if (!h) return fail(BSREG_EINVAL, "null handle");
+  if (re) std::copy(h->node_re.begin(), h->node_re.end(), re);
+  if (im) std::copy(h->node_im.begin(), h->node_im.end(), im);
+  if (w) std::copy(h->node_w.begin(), h->node_w.end(), w);
+  return BSREG_OK;
+}
+
+int bsreg_eval_trace_moments(bsreg_handle *h, int32_t order, int32_t n_probes, uint64_t seed, double *moments) {
+  if (!h || !moments || order < 0 || n_probes <= 0) return fail(BSREG_EINVAL, "bad argument");
+  Shard &s = h->shards[0];
+  if (!s.dd.rp) return fail(BSREG_EINVAL, "handle has no W");
+  CU(cudaSetDevice(s.dev));
+  // host copy of the CSR for the exact low-order traces
+  std::vector<int32_t> rp((size_t)h->n + 1), ci((size_t)h->nnz);
+  std::vector<double> va((size_t)h->nnz);
+  CU(cudaMemcpy(rp.data(), s.dd.rp, rp.size() * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(ci.data(), s.dd.ci, ci.size() * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(va.data(), s.dd.va, va.size() * 8, cudaMemcpyDeviceToHost));
+  bsreg_problem p{};
+  p.row_ptr = rp.data(); p.col_idx = ci.data(); p.val = va.data();
+  return trace_moments_dev(h, s, &p, order, n_probes, seed, moments);
+}
+
+int bsreg_eval_conditionals(bsreg_handle *h, int32_t n_eval, const double *beta, const double *sigma2, const double *lam,
+                            const double *p0, const double *v, double *mu1, double *rate1, double *rss, double *logpost) {
+  if (!h || n_eval <= 0 || !beta || !sigma2 || !lam || !p0 || !v) return fail(BSREG_EINVAL, "bad argument");
+  Shard &s = h->shards[0];
+  CU(cudaSetDevice(s.dev));
+  const size_t ne = n_eval, m = h->m;
+  double *buf;
+  CU(cudaMalloc(&buf, (ne * m * 3 + ne * 6) * 8));
+  double *db = buf, *dp0 = db + ne * m, *dmu1 = dp0 + ne * m, *ds2 = dmu1 + ne * m, *dl = ds2 + ne, *dv = dl + ne,
+         *drate = dv + ne, *drss = drate + ne, *dlp = drss + ne;
+  CU(cudaMemcpyAsync(db, beta, ne * m * 8, cudaMemcpyHostToDevice, s.stream));
+  CU(cudaMemcpyAsync(dp0, p0, ne * m * 8, cudaMemcpyHostToDevice, s.stream));
+  CU(cudaMemcpyAsync(ds2, sigma2, ne * 8, cudaMemcpyHostToDevice, s.stream));
+  CU(cudaMemcpyAsync(dl, lam, ne * 8, cudaMemcpyHostToDevice, s.stream));
+  CU(cudaMemcpyAsync(dv, v, ne * 8, cudaMemcpyHostToDevice, s.stream));
+  launch_eval_conditionals(s.dd, h->pr, s.cs.mu0, n_eval, db, ds2, dl, dp0, dv, dmu1, drate, drss, dlp, s.stream);
+  ++h->launches;
+  CU(cudaGetLastError());
+  if (mu1) CU(cudaMemcpyAsync(mu1, dmu1, ne * m * 8, cudaMemcpyDeviceToHost, s.stream));
+  if (rate1) CU(cudaMemcpyAsync(rate1, drate, ne * 8, cudaMemcpyDeviceToHost, s.stream));
+  if (rss) CU(cudaMemcpyAsync(rss, drss, ne * 8, cudaMemcpyDeviceToHost, s.stream));
+  if (logpost) CU(cudaMemcpyAsync(logpost, dlp, ne * 8, cudaMemcpyDeviceToHost, s.stream));
+  CU(cudaStreamSynchronize(s.stream));
+  cudaFree(buf);
+  return BSREG_OK;
+}
+
+int bsreg_eval_rng(int32_t kind, uint64_t seed, int32_t chain, int32_t slot, int32_t it0, int32_t n, const double *params,
+                   double *out) {
+  if (!out || n <= 0 || kind < 0 || kind > 5) return fail(BSREG_EINVAL, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(BSREG_ENOGPU, "no CUDA device available"); }
+  double *dp, *dout;
+  CU(cudaMalloc(&dp, 4 * 8)); CU(cudaMalloc(&dout, (size_t)n * 8));
+  double hp[4] = {0, 0, 0, 0};
+  const int np = kind == 2 ? 2 : kind == 3 ? 1 : kind == 4 ? 3 : kind == 5 ? 4 : 0;
+  for (int i = 0; i < np; ++i) hp[i] = params ? params[i] : 0.0;
+  CU(cudaMemcpy(dp, hp, sizeof hp, cudaMemcpyHostToDevice));
+  launch_eval_rng(kind, seed, chain, slot, it0, n, dp, dout, 0);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dp); cudaFree(dout);
+  return BSREG_OK;
+}
+
+// ---- measurement helpers ----
+void *bsreg_stream(bsreg_handle *h) { return h ? (void *)h->shards[0].stream : nullptr; }
+
+int bsreg_launch_sweep(bsreg_handle *h, int32_t reps) {
+  if (!h) return fail(BSREG_EINVAL, "null handle");
+  Shard &s = h->shards[0];
+  CU(cudaSetDevice(s.dev));
+  for (int i = 0; i < reps; ++i) launch_sweep(s.dd, s.sm_count, s.stream);
+  h->launches += reps;
+  CU(cudaGetLastError());
+  return BSREG_OK;
+}
+
+int bsreg_launch_chain_step(bsreg_handle *h, int32_t reps) {
+  if (!h) return fail(BSREG_EINVAL, "null handle");
+  Shard &s = h->shards[0];
+  CU(cudaSetDevice(s.dev));
+  RunCtl ctl{};
+  ctl.n_burn = 1 << 30; ctl.tune_limit = 0; ctl.store = 0; ctl.acc_lo = 0.2; ctl.acc_hi = 0.45; ctl.acc_change = 0.8;
+  CU(cudaMemcpyAsync(s.ctl_dev, &ctl, sizeof ctl, cudaMemcpyHostToDevice, s.stream));
+  for (int i = 0; i < reps; ++i) launch_chain_step(s.dd, h->pr, s.cs, s.ctl_dev, s.draws_dev, s.stream);
+  h->launches += reps;
+  CU(cudaGetLastError());
+  return BSREG_OK;
+}
+
+int bsreg_sync(bsreg_handle *h) {
+  if (!h) return fail(BSREG_EINVAL, "null handle");
+  for (Shard &s : h->shards) { CU(cudaSetDevice(s.dev)); CU(cudaStreamSynchronize(s.stream)); }
+  return BSREG_OK;
+}
+
+// CSR once (12 nnz + 4 (N+1)) + y and X once (8 N (K+1))
+int64_t bsreg_sweep_bytes(const bsreg_handle *h) {
+  if (!h) return 0;
+  const int64_t w = h->model == BSREG_MODEL_LM ? 0 : 12 * h->nnz + 4 * ((int64_t)h->n + 1);
+  return w + 8 * (int64_t)h->n * (h->m + 1);
+}
+
+int64_t bsreg_kernel_launches(const bsreg_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

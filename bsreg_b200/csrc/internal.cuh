@@ -1,0 +1,99 @@
+// Internal declarations shared by the kernel files and the C-ABI host code.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bsreg {
+
+// ---------------------------------------------------------------------------
+// Problem data resident in HBM (one replica per GPU).
+//   X     row-major [n][m]   (m includes SLX-lagged columns)
+//   y     [n]
+//   W     CSR: rp int32 [n+1], ci int32 [nnz], va f64 [nnz]
+//   G     f64 [d][d] symmetric Gram of Z = [y | Wy | X | WX]
+//         d = m + 2 (LM: Wy column is zero; SAR) or 2m + 2 (SEM)
+//   Gfix  int64 fixed-point accumulators behind G (order-independent atomics)
+// ---------------------------------------------------------------------------
+struct DeviceData {
+  int n, m, d, model;
+  int64_t nnz;
+  const int *rp, *ci;
+  const double *va;
+  const double *y, *X;
+  double *Wy, *WX;            // cached lags (R/15_sar.R:57, R/15_sem.R:63-64): direct-form kernel, generic sweep
+  double *G;                  // d*d
+  long long *Gfix;            // d*d, zero between sweeps
+  const double *Gscale;       // d*d: value = Gfix * Gscale  (power of two)
+  const double *Ginv_scale;   // d*d: fixed = rint(value * Ginv_scale)
+  unsigned int *ticket;       // sweep completion counter
+  // log-determinant nodes
+  int n_nodes;
+  const double *node_re, *node_im, *node_w;
+};
+
+struct Priors {
+  int prior;
+  double shape0, rate0, shape1;
+  double sng_lambda_a, sng_lambda_b, sng_theta_scale, sng_theta_a;
+  double lam_a, lam_b, lam_lo, lam_hi, lbeta_ab;   // spatial lambda prior + bounds
+};
+
+// Per-chain state, structure of arrays over the C chains of this GPU.
+struct ChainState {
+  int n_chains, chain_offset;
+  uint64_t seed;
+  double *beta;        // [C][m]
+  double *sigma2;      // [C]
+  double *lam;         // [C]
+  double *p0;          // [C][m]   prior precision diagonal
+  double *aux;         // [C][A]   A = 2m + 4: vecA[m], vecB[m], s0, s1, ldet_cur, rss_cur
+  double *mh_scale;    // [C][2]   0 = spatial lambda, 1 = SNG theta
+  long long *mh_cnt;   // [C][2][4] accepted, proposed, accepted_tune, proposed_tune
+  long long *iters;    // [C]      R/10_lm.R:75 meta$iterations
+  int *step;           // [C]      iteration index inside the current bsreg_run
+  const double *mu0;   // [m]      prior mean
+};
+
+struct RunCtl {        // lives in device memory; updated by the host between blocks
+  int n_burn, tune_limit, n_save, save_base, save_cap, store;
+  double acc_lo, acc_hi, acc_change;
+};
+
+constexpr int AUX_EXTRA = 4;
+__host__ __device__ inline int aux_len(int m) { return 2 * m + AUX_EXTRA; }
+
+// launchers (sweep.cu)
+void launch_transpose(const double *src_colmajor, double *dst_rowmajor, int n, int m, int ld_dst, int col0, cudaStream_t s);
+void launch_spmm(int n, const int *rp, const int *ci, const double *va, const double *B, int m, int ldb,
+                 double *out, int ldo, int col0, double alpha, const double *C, double beta, cudaStream_t s);
+void launch_colnorms(const DeviceData &dd, double *norms, cudaStream_t s);
+bool sweep_fast_supported(const DeviceData &dd);
+void launch_sweep(const DeviceData &dd, int sm_count, cudaStream_t s);
+int  sweep_launch_count();
+void launch_residual_ss(const DeviceData &dd, int n_eval, const double *beta,
+                        const double *lam, const double *rho, double *partial, double *out, cudaStream_t s);
+void launch_probes(double *U, int n, int n_probes, uint64_t seed, cudaStream_t s);
+void launch_dot(const double *a, const double *b, int64_t len, double *partial, double *out, cudaStream_t s);
+
+// launchers (chain.cu)
+size_t chain_smem_bytes(int m, int model, int prior);
+int  chain_threads(int m);
+struct ChainInit {
+  const double *beta0;     // device [m] or null (least squares)
+  double sigma0;           // NaN = RSS/(N-M)
+  double lam0, scale0;
+  double hs_lambda, hs_tau, hs_zeta, hs_nu, sng_lambda, sng_tau, sng_theta, sng_theta_scale;
+  const double *p0_init;   // device [m]
+  bool refresh_only;       // only recompute the cached log-det / rss at the current lambda
+};
+void launch_chain_init(const DeviceData &dd, const Priors &pr, const ChainState &cs, const ChainInit &ci, cudaStream_t s);
+void launch_chain_step(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl *ctl, double *draws,
+                       cudaStream_t s);
+void launch_eval_logdet(const DeviceData &dd, int n_eval, const double *v, double *out, cudaStream_t s);
+void launch_eval_conditionals(const DeviceData &dd, const Priors &pr, const double *mu0, int n_eval, const double *beta,
+                              const double *sigma2, const double *lam, const double *p0, const double *v, double *mu1,
+                              double *rate1, double *rss, double *logpost, cudaStream_t s);
+void launch_eval_rng(int kind, uint64_t seed, int chain, int slot, int it0, int n, const double *params, double *out,
+                     cudaStream_t s);
+
+}  // namespace bsreg

@@ -1,0 +1,437 @@
+// N-scale kernels of the Gibbs hot path (hand-written for sm_100a, FP64, no tensor cores):
+//
+//   K1  csr_spmm_kernel      W*B for dense row-major B        (R/15_sar.R:57, R/15_sem.R:63-64, R/12_slx.R:65)
+//   K1+K2 sweep_gram_kernel  ONE pass over W, y, X per Gibbs iteration: forms the spatial lags
+//                            Wy (and WX) on the fly and accumulates G = Z'Z, Z = [y|Wy|X|WX]
+//                            (R/10_lm.R:36, R/15_sar.R:133-135, R/15_sem.R:34-35 and every
+//                             N-scale quadratic form of R/10_lm.R:176, R/15_sar.R:110-114,
+//                             R/15_sem.R:116-120 are polynomials in lambda of blocks of G)
+//   K2  residual_ss_kernel   direct per-parameter-set ||(y - lam Wy) - (X - rho WX) beta||^2 with
+//                            warp-shuffle + block reductions (R/10_lm.R:176,192)
+//   K4  probes / dot         Rademacher probes and u'T_j(W)u dots for the trace moments
+//
+// All reductions are bit-reproducible: fixed-order trees inside a CTA, and 64-bit
+// fixed-point integer atomics across CTAs (integer addition is associative, so the
+// result does not depend on CTA arrival order).
+#include "internal.cuh"
+#include "rng.cuh"
+
+namespace bsreg {
+
+static int g_sweep_launches = 0;
+int sweep_launch_count() { return g_sweep_launches; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// layout helpers
+// ---------------------------------------------------------------------------
+__global__ void transpose_kernel(const double *__restrict__ src, double *__restrict__ dst, int n, int m, int ld, int col0) {
+  __shared__ double tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {   // src column-major: element (r, c) at c*n + r
+    const int r = r0 + threadIdx.x, c = c0 + j;
+    tile[j][threadIdx.x] = (r < n && c < m) ? src[(size_t)c * n + r] : 0.0;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < n && c < m) dst[(size_t)r * ld + col0 + c] = tile[threadIdx.x][j];
+  }
+}
+
+void launch_transpose(const double *src, double *dst, int n, int m, int ld, int col0, cudaStream_t s) {
+  dim3 grid((n + 31) / 32, (m + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, s>>>(src, dst, n, m, ld, col0);
+}
+
+// ---------------------------------------------------------------------------
+// K1: out[i, col0 + c] = alpha * sum_p va[p] * B[ci[p], c] + beta * C[i, col0 + c]
+// one thread per (row, column); consecutive threads read consecutive columns of a
+// gathered row, so the gather is coalesced for m >= 4.
+// ---------------------------------------------------------------------------
+__global__ void csr_spmm_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci,
+                                const double *__restrict__ va, const double *__restrict__ B, int m, int ldb,
+                                double *__restrict__ out, int ldo, int col0, double alpha,
+                                const double *__restrict__ C, double beta) {
+  const size_t total = (size_t)n * m;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / m), c = (int)(idx % m);
+    double acc = 0.0;
+    for (int p = rp[row], pe = rp[row + 1]; p < pe; ++p) acc = fma(va[p], B[(size_t)ci[p] * ldb + c], acc);
+    double v = alpha * acc;
+    if (C != nullptr) v += beta * C[(size_t)row * ldo + col0 + c];
+    out[(size_t)row * ldo + col0 + c] = v;
+  }
+}
+
+void launch_spmm(int n, const int *rp, const int *ci, const double *va, const double *B, int m, int ldb, double *out,
+                 int ldo, int col0, double alpha, const double *C, double beta, cudaStream_t s) {
+  const size_t total = (size_t)n * m;
+  const int block = 256;
+  const int grid = (int)((total + block - 1) / block < 148 * 16 ? (total + block - 1) / block : 148 * 16);
+  csr_spmm_kernel<<<grid > 0 ? grid : 1, block, 0, s>>>(n, rp, ci, va, B, m, ldb, out, ldo, col0, alpha, C, beta);
+}
+
+// ---------------------------------------------------------------------------
+// column sums of squares of Z (setup only; fixes the fixed-point scales)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double z_entry(const DeviceData &dd, int row, int c) {
+  if (c == 0) return dd.y[row];
+  if (c == 1) return dd.Wy ? dd.Wy[row] : 0.0;
+  if (c < 2 + dd.m) return dd.X[(size_t)row * dd.m + c - 2];
+  return dd.WX[(size_t)row * dd.m + c - 2 - dd.m];
+}
+
+__global__ void colnorm_kernel(DeviceData dd, double *norms) {
+  __shared__ double red[256];
+  const int c = blockIdx.x;
+  double acc = 0.0;
+  for (int row = threadIdx.x; row < dd.n; row += blockDim.x) {
+    const double v = z_entry(dd, row, c);
+    acc = fma(v, v, acc);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) norms[c] = red[0];
+}
+
+void launch_colnorms(const DeviceData &dd, double *norms, cudaStream_t s) {
+  colnorm_kernel<<<dd.d, 256, 0, s>>>(dd, norms);
+}
+
+// ---------------------------------------------------------------------------
+// K1 + K2 fused sweep (fast path, d <= 88).
+//
+// A CTA stages a tile of R rows of Z in shared memory (X and y streamed from HBM
+// exactly once, Wy/WX gathered through W), then accumulates Z_tile' Z_tile in
+// registers: the upper triangle of G is cut into 4x4 blocks, thread = (block,
+// row group).  Lanes of a warp hold different blocks of the SAME row, so the
+// shared-memory reads are broadcasts, and each thread issues 16 DFMA per 4
+// LDS.128.  CTAs are persistent (grid = SMs x occupancy, static tile->CTA map).
+// ---------------------------------------------------------------------------
+template <int NB>
+struct SweepCfg {
+  static constexpr int B = NB * (NB + 1) / 2;
+  static constexpr int RG = (B > 128) ? 1 : (256 + B / 2) / B;
+  static constexpr int T = ((B * RG + 31) / 32) * 32;
+  static constexpr int RPT = (64 + RG / 2) / RG > 0 ? (64 + RG / 2) / RG : 1;
+  static constexpr int R = RG * RPT;
+  static constexpr int DP = 4 * NB;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(SweepCfg<NB>::T) sweep_gram_kernel(DeviceData dd, int ntiles) {
+  using Cfg = SweepCfg<NB>;
+  constexpr int B = Cfg::B, RG = Cfg::RG, T = Cfg::T, RPT = Cfg::RPT, R = Cfg::R, DP = Cfg::DP;
+  __shared__ __align__(16) double Z[R * DP];
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int m = dd.m, d = dd.d, n = dd.n;
+  const bool sem = dd.model == 2, has_w = dd.model != 0;
+
+  // thread -> (block of G, row group)
+  const int blk = tid % B, rg = tid / B;
+  const bool active = rg < RG;
+  int bi = 0, bj = blk;
+  while (bj >= NB - bi) { bj -= NB - bi; ++bi; }
+  bj += bi;                                   // bi <= bj < NB
+
+  double acc[4][4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int r0 = tile * R;
+    // ---- phase A1: stream y and X rows (coalesced), zero the padding ----
+    for (int e = tid; e < R * DP; e += T) {
+      const int r = e / DP, c = e - r * DP;
+      const int row = r0 + r;
+      if (c == 1 || (sem && c >= 2 + m && c < 2 + 2 * m)) continue;   // lag columns are written below
+      double v = 0.0;
+      if (row < n) {
+        if (c == 0) v = dd.y[row];
+        else if (c < 2 + m) v = dd.X[(size_t)row * m + (c - 2)];
+      }
+      Z[e] = v;
+    }
+    // ---- phase A2: Wy, four lanes per row, fixed-order combine ----
+    for (int rb = wid * 8; rb < R; rb += (T / 32) * 8) {
+      const int r = rb + (lane >> 2), q = lane & 3;
+      const int row = r0 + r;
+      double s = 0.0;
+      if (has_w && r < R && row < n) {
+        for (int p = dd.rp[row] + q, pe = dd.rp[row + 1]; p < pe; p += 4) s = fma(dd.va[p], dd.y[dd.ci[p]], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (q == 0 && r < R) Z[r * DP + 1] = s;
+    }
+    // ---- phase A3 (SEM): WX, one thread per (row, column), coalesced row gathers ----
+    if (sem) {
+      for (int e = tid; e < R * m; e += T) {
+        const int r = e / m, c = e - r * m;
+        const int row = r0 + r;
+        double s = 0.0;
+        if (row < n) {
+          for (int p = dd.rp[row], pe = dd.rp[row + 1]; p < pe; ++p)
+            s = fma(dd.va[p], dd.X[(size_t)dd.ci[p] * m + c], s);
+        }
+        Z[r * DP + 2 + m + c] = s;
+      }
+    }
+    __syncthreads();
+    // ---- phase B: rank-R update of the 4x4 register block ----
+    if (active) {
+#pragma unroll 4
+      for (int i = 0; i < RPT; ++i) {
+        const double *zr = Z + (rg + i * RG) * DP;
+        const double2 a01 = *reinterpret_cast<const double2 *>(zr + 4 * bi);
+        const double2 a23 = *reinterpret_cast<const double2 *>(zr + 4 * bi + 2);
+        const double2 b01 = *reinterpret_cast<const double2 *>(zr + 4 * bj);
+        const double2 b23 = *reinterpret_cast<const double2 *>(zr + 4 * bj + 2);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[p][q] = fma(a[p], b[q], acc[p][q]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- combine the row groups of this CTA in fixed order ----
+  if (RG > 1) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        Z[tid] = active ? acc[p][q] : 0.0;
+        __syncthreads();
+        if (rg == 0) {
+          double s = 0.0;
+          for (int g = 0; g < RG; ++g) s += Z[blk + g * B];
+          acc[p][q] = s;
+        }
+        __syncthreads();
+      }
+  }
+  // ---- order-independent accumulation across CTAs: 64-bit fixed point ----
+  if (rg == 0) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int gi = 4 * bi + p, gj = 4 * bj + q;
+        if (gi < d && gj < d && gi <= gj) {
+          const long long f = __double2ll_rn(acc[p][q] * dd.Ginv_scale[gi * d + gj]);
+          atomicAdd(reinterpret_cast<unsigned long long *>(dd.Gfix + gi * d + gj), (unsigned long long)f);
+        }
+      }
+  }
+  // ---- last CTA converts to double, mirrors, and re-zeroes the accumulators ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(dd.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int e = tid; e < d * d; e += T) {
+      const int i = e / d, j = e - i * d;
+      if (i <= j) {
+        const long long f = __ldcg(dd.Gfix + e);
+        const double v = (double)f * dd.Gscale[e];
+        dd.G[i * d + j] = v;
+        dd.G[j * d + i] = v;
+        dd.Gfix[e] = 0;
+      }
+    }
+    if (tid == 0) *dd.ticket = 0u;
+  }
+}
+
+// generic path (any d): one warp per entry of the upper triangle over materialised lags
+__global__ void gram_generic_kernel(DeviceData dd) {
+  const int d = dd.d;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total = d * (d + 1) / 2;
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total; e += warps) {
+    int i = 0, j = e;
+    while (j >= d - i) { j -= d - i; ++i; }
+    j += i;
+    double acc = 0.0;
+    for (int row = lane; row < dd.n; row += 32)
+      acc = fma(z_entry(dd, row, i), z_entry(dd, row, j), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) { dd.G[i * d + j] = acc; dd.G[j * d + i] = acc; }
+  }
+}
+
+bool sweep_fast_supported(const DeviceData &dd) { return dd.d <= 88; }
+
+template <int NB>
+static void launch_sweep_nb(const DeviceData &dd, int sm_count, cudaStream_t s) {
+  using Cfg = SweepCfg<NB>;
+  static int occ = 0;
+  if (occ == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sweep_gram_kernel<NB>, Cfg::T, 0);
+    if (occ < 1) occ = 1;
+    if (occ > 4) occ = 4;
+  }
+  const int ntiles = (dd.n + Cfg::R - 1) / Cfg::R;
+  int grid = sm_count * occ;
+  if (grid > ntiles) grid = ntiles;
+  sweep_gram_kernel<NB><<<grid, Cfg::T, 0, s>>>(dd, ntiles);
+}
+
+void launch_sweep(const DeviceData &dd, int sm_count, cudaStream_t s) {
+  ++g_sweep_launches;
+  if (!sweep_fast_supported(dd)) {   // wide designs (d > 88): refresh the lags through W, then one warp per entry
+    if (dd.model != 0) launch_spmm(dd.n, dd.rp, dd.ci, dd.va, dd.y, 1, 1, dd.Wy, 1, 0, 1.0, nullptr, 0.0, s);
+    if (dd.model == 2) launch_spmm(dd.n, dd.rp, dd.ci, dd.va, dd.X, dd.m, dd.m, dd.WX, dd.m, 0, 1.0, nullptr, 0.0, s);
+    gram_generic_kernel<<<296, 256, 0, s>>>(dd);
+    return;
+  }
+  const int nb = (dd.d + 3) / 4;
+  if (nb <= 2) launch_sweep_nb<2>(dd, sm_count, s);
+  else if (nb <= 3) launch_sweep_nb<3>(dd, sm_count, s);
+  else if (nb <= 4) launch_sweep_nb<4>(dd, sm_count, s);
+  else if (nb <= 6) launch_sweep_nb<6>(dd, sm_count, s);
+  else if (nb <= 8) launch_sweep_nb<8>(dd, sm_count, s);
+  else if (nb <= 11) launch_sweep_nb<11>(dd, sm_count, s);
+  else if (nb <= 16) launch_sweep_nb<16>(dd, sm_count, s);
+  else launch_sweep_nb<22>(dd, sm_count, s);
+}
+
+// ---------------------------------------------------------------------------
+// K2 direct form: one warp per row, lanes over regressors, shuffle reduction per
+// row, block reduction per CTA, fixed-order combine over CTAs.
+// ---------------------------------------------------------------------------
+constexpr int RSS_EC = 4;          // evaluations per pass
+constexpr int RSS_GRID = 592;      // CTAs (4 per SM)
+
+__global__ void __launch_bounds__(256) residual_ss_kernel(DeviceData dd, int e0, int n_eval,
+                                                          const double *__restrict__ beta,
+                                                          const double *__restrict__ lam,
+                                                          const double *__restrict__ rho, double *partial) {
+  extern __shared__ double sb[];            // beta chunk [RSS_EC][m]
+  __shared__ double red[8][RSS_EC];
+  const int m = dd.m, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const double *__restrict__ Wy = dd.Wy;
+  const double *__restrict__ WX = dd.model == 2 ? dd.WX : nullptr;
+  const int ne = min(RSS_EC, n_eval - e0);
+  for (int i = threadIdx.x; i < ne * m; i += blockDim.x) sb[i] = beta[(size_t)e0 * m + i];
+  double l[RSS_EC], r[RSS_EC], acc[RSS_EC];
+#pragma unroll
+  for (int e = 0; e < RSS_EC; ++e) {
+    l[e] = e < ne ? lam[e0 + e] : 0.0;
+    r[e] = e < ne ? rho[e0 + e] : 0.0;
+    acc[e] = 0.0;
+  }
+  __syncthreads();
+  const int warps = gridDim.x * 8;
+  for (int row = blockIdx.x * 8 + wid; row < dd.n; row += warps) {
+    double part[RSS_EC];
+#pragma unroll
+    for (int e = 0; e < RSS_EC; ++e) part[e] = 0.0;
+    for (int a = lane; a < m; a += 32) {
+      const double x = dd.X[(size_t)row * m + a];
+      const double wx = WX ? WX[(size_t)row * m + a] : 0.0;
+#pragma unroll
+      for (int e = 0; e < RSS_EC; ++e)
+        if (e < ne) part[e] = fma(x - r[e] * wx, sb[e * m + a], part[e]);
+    }
+    const double yv = dd.y[row], wy = Wy ? Wy[row] : 0.0;
+#pragma unroll
+    for (int e = 0; e < RSS_EC; ++e) {
+      const double res = (yv - l[e] * wy) - warp_sum(part[e]);
+      acc[e] = fma(res, res, acc[e]);
+    }
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int e = 0; e < RSS_EC; ++e) red[wid][e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < RSS_EC) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * RSS_EC + threadIdx.x] = s;
+  }
+}
+
+__global__ void combine_partials_kernel(const double *partial, int nparts, int stride, int count, double *out) {
+  const int e = threadIdx.x;
+  if (e < count) {
+    double s = 0.0;
+    for (int b = 0; b < nparts; ++b) s += partial[(size_t)b * stride + e];
+    out[e] = s;
+  }
+}
+
+void launch_residual_ss(const DeviceData &dd, int n_eval, const double *beta,
+                        const double *lam, const double *rho, double *partial, double *out, cudaStream_t s) {
+  for (int e0 = 0; e0 < n_eval; e0 += RSS_EC) {
+    residual_ss_kernel<<<RSS_GRID, 256, RSS_EC * dd.m * sizeof(double), s>>>(dd, e0, n_eval, beta, lam, rho, partial);
+    const int ne = n_eval - e0 < RSS_EC ? n_eval - e0 : RSS_EC;
+    combine_partials_kernel<<<1, 32, 0, s>>>(partial, RSS_GRID, RSS_EC, ne, out + e0);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4 helpers: Rademacher probes (same bits as oracle/core.py:rademacher_probes) and dots
+// ---------------------------------------------------------------------------
+__global__ void probes_kernel(double *U, int n, int n_probes, uint64_t seed) {
+  const int nb = (n_probes + 127) / 128;
+  const Philox ph(seed, 0xffffffffu);
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)n * nb; idx += (size_t)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / nb), b = (int)(idx % nb);
+    const uint4 r = ph.raw((uint32_t)row, SLOT_PROBE, (uint32_t)b, 0xffffffffu);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    for (int k = 0; k < 4; ++k)
+      for (int j = 0; j < 32; ++j) {
+        const int p = 128 * b + 32 * k + j;
+        if (p < n_probes) U[(size_t)row * n_probes + p] = 1.0 - 2.0 * (double)((w[k] >> j) & 1u);
+      }
+  }
+}
+
+void launch_probes(double *U, int n, int n_probes, uint64_t seed, cudaStream_t s) {
+  probes_kernel<<<592, 256, 0, s>>>(U, n, n_probes, seed);
+}
+
+constexpr int DOT_GRID = 592;
+__global__ void __launch_bounds__(256) dot_kernel(const double *__restrict__ a, const double *__restrict__ b, int64_t len,
+                                                  double *partial) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+    acc = fma(a[i], b[i], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    partial[blockIdx.x] = s;
+  }
+}
+
+void launch_dot(const double *a, const double *b, int64_t len, double *partial, double *out, cudaStream_t s) {
+  dot_kernel<<<DOT_GRID, 256, 0, s>>>(a, b, len, partial);
+  combine_partials_kernel<<<1, 32, 0, s>>>(partial, DOT_GRID, 1, 1, out);
+}
+
+}  // namespace bsreg

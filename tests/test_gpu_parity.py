@@ -1,0 +1,192 @@
+"""CUDA path vs oracle on the same seeded inputs, through the C ABI.  Tolerances:
+1e-10 relative for the deterministic kernels, 1e-8 for log-determinants (north_star)."""
+import numpy as np
+import pytest
+
+from oracle import core
+from oracle.philox import Slot, Stream
+from tests.helpers import cuda_handle, oracle_chain, oracle_draws, small_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def relnorm(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.mark.parametrize("model", ["sar", "sem"])
+def test_spmm_and_gram(model):
+    p = small_problem(model, n=1037, k=7)
+    with cuda_handle(model, p) as h:
+        B = np.random.default_rng(0).standard_normal((p.X.shape[0], 5))
+        assert relnorm(h.eval_spmm(B), core.spmm(p.W, B)) < 1e-13
+        Wy = core.spmm(p.W, p.y)
+        WX = core.spmm(p.W, p.X) if model == "sem" else None
+        G_ref = core.gram(p.y, p.X, Wy, WX)
+        G = h.eval_gram()
+        assert G.shape == G_ref.shape
+        scale = np.sqrt(np.outer(np.diag(G_ref), np.diag(G_ref)))
+        assert np.max(np.abs(G - G_ref) / scale) < 1e-13
+        assert np.array_equal(G, G.T)
+        assert np.array_equal(G, h.eval_gram())          # bit-reproducible
+
+
+def test_gram_lm():
+    p = small_problem("lm", n=777, k=3)
+    with cuda_handle("lm", p) as h:
+        G = h.eval_gram()
+        G_ref = core.gram(p.y, p.X, np.zeros_like(p.y), None)
+        assert np.max(np.abs(G - G_ref)) / np.max(np.abs(G_ref)) < 1e-13
+
+
+@pytest.mark.parametrize("model", ["lm", "sar", "sem"])
+def test_residual_ss_direct(model):
+    p = small_problem(model, n=901, k=6)
+    rng = np.random.default_rng(1)
+    with cuda_handle(model, p) as h:
+        ne = 7
+        beta = p.beta + 0.1 * rng.standard_normal((ne, len(p.beta)))
+        lam = rng.uniform(-0.5, 0.9, ne) if model != "lm" else np.zeros(ne)
+        rho = lam if model == "sem" else np.zeros(ne)
+        got = h.eval_residual_ss(beta, lam, rho)
+        Wy = core.spmm(p.W, p.y) if model != "lm" else np.zeros_like(p.y)
+        WX = core.spmm(p.W, p.X) if model == "sem" else np.zeros_like(p.X)
+        want = [core.residual_ss(p.y, p.X, Wy, WX, beta[e], lam[e], rho[e]) for e in range(ne)]
+        assert rel(got, want) < 1e-10
+
+
+def test_logdet_eigen_real_and_complex():
+    for symmetric in (True, False):
+        p = small_problem("sar", n=300, k=3, symmetric=symmetric)
+        nodes = core.eigen_nodes(p.W, 1)
+        with cuda_handle("sar", p, nodes=nodes) as h:
+            v = np.linspace(-0.95, 0.98, 41)
+            want = np.array([core.ldet_nodes(x, *nodes) for x in v])
+            got = h.eval_logdet(v)
+            assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1.0)) < 1e-8
+            dense = np.array([core.ldet_dense(x, p.W) for x in v[::8]])
+            assert np.max(np.abs(got[::8] - dense) / np.maximum(np.abs(dense), 1.0)) < 1e-8
+
+
+@pytest.mark.parametrize("model", ["sar", "sem"])
+def test_conditionals(model):
+    p = small_problem(model, n=650, k=5)
+    rng = np.random.default_rng(3)
+    nodes = core.eigen_nodes(p.W, 1)
+    with cuda_handle(model, p, nodes=nodes) as h:
+        ne, m = 6, p.X.shape[1]
+        beta = p.beta + 0.05 * rng.standard_normal((ne, m))
+        s2 = rng.uniform(0.5, 2.0, ne)
+        lam = rng.uniform(-0.3, 0.8, ne)
+        v = rng.uniform(-0.3, 0.8, ne)
+        p0 = rng.uniform(1e-8, 2.0, (ne, m))
+        got = h.eval_conditionals(beta, s2, lam, p0, v)
+        Wy, WX = core.spmm(p.W, p.y), core.spmm(p.W, p.X)
+        for e in range(ne):
+            if model == "sar":
+                ys, Xs = p.y - lam[e] * Wy, p.X
+            else:
+                ys, Xs = p.y - lam[e] * Wy, p.X - lam[e] * WX
+            _, mu1 = core.beta_moments(Xs.T @ Xs, Xs.T @ ys, s2[e], p0[e], np.zeros(m))
+            assert relnorm(got["mu1"][e], mu1) < 1e-10
+            rate1 = 0.01 + 0.5 * core.sq_sum(ys - Xs @ beta[e])
+            assert abs(got["rate1"][e] - rate1) / rate1 < 1e-10
+            if model == "sar":
+                c = core.sar_rss_coeffs(p.y, Wy, p.X, p.X.T @ p.X, s2[e], p0[e], np.zeros(m))
+                rss = c[0] - 2 * v[e] * c[1] + v[e] ** 2 * c[2]
+            else:
+                rss = core.sem_rss(v[e], p.y, Wy, p.X, WX)
+            assert abs(got["rss"][e] - rss) / rss < 1e-10
+            lp = core.logpost_lambda(v[e], core.ldet_nodes(v[e], *nodes), rss, len(p.y), m, 1.01, 1.01)
+            assert abs(got["logpost"][e] - lp) / abs(lp) < 1e-10
+
+
+def test_device_rng_matches_contract(capi):
+    s = Stream(seed=0x1234567890ABCDEF, chain=5)
+    n = 64
+    u = capi.eval_rng(0, 0x1234567890ABCDEF, 5, Slot.LAMBDA_ACC, 1, n)
+    assert np.array_equal(u, [s.uniform(1 + i, Slot.LAMBDA_ACC) for i in range(n)])
+    z = capi.eval_rng(1, 0x1234567890ABCDEF, 5, Slot.BETA, 1, n)
+    assert rel(z, [s.normal(1 + i, Slot.BETA) for i in range(n)]) < 1e-12
+    for shape, rate in [(50000.01, 3.0), (2.5, 0.7), (0.3, 2.0), (1.0, 4.0)]:
+        g = capi.eval_rng(2, 0x1234567890ABCDEF, 5, Slot.SIGMA, 1, n, (shape, rate))
+        assert rel(g, [s.gamma(1 + i, Slot.SIGMA, shape, rate) for i in range(n)]) < 1e-11
+    for lam, chi, psi in [(-0.4, 0.3, 0.1), (-0.4, 1e-4, 0.05), (0.5, 2.0, 3.0), (3.0, 1.0, 1.0), (-0.4, 30.0, 2.0)]:
+        g = capi.eval_rng(4, 0x1234567890ABCDEF, 5, Slot.SNG_TAU, 1, n, (lam, chi, psi))
+        assert rel(g, [s.gig(1 + i, Slot.SNG_TAU, lam, chi, psi) for i in range(n)]) < 1e-10
+    t = capi.eval_rng(5, 0x1234567890ABCDEF, 5, Slot.LAMBDA_PROP, 1, n, (0.95, 0.2, -1.0, 1 - 1e-12))
+    assert rel(t, [s.truncated_rw(1 + i, Slot.LAMBDA_PROP, 0.95, 0.2, -1.0, 1 - 1e-12) for i in range(n)]) < 1e-12
+
+
+CASES = [("lm", "Independent"), ("sar", "Independent"), ("sem", "Independent"),
+         ("lm", "Conjugate"), ("sar", "Conjugate"), ("sem", "Conjugate"),
+         ("lm", "Horseshoe"), ("sar", "Horseshoe"), ("sem", "Horseshoe"),
+         ("lm", "Shrinkage"), ("sar", "Shrinkage"), ("sem", "Shrinkage")]
+
+
+@pytest.mark.parametrize("model,prior", CASES)
+def test_chain_trajectory_matches_oracle(model, prior):
+    """Same Philox stream => the CUDA chain must reproduce the oracle chain draw by draw
+    (burn-in with MH tuning included)."""
+    p = small_problem(model, n=500, k=4)
+    priors = {"SNG": dict(theta_scale=0.3)} if prior == "Shrinkage" else {}
+    n_burn, n_save, chain_id = 60, 80, 3
+    ref = oracle_draws(oracle_chain(model, p, prior, priors, seed=99, chain=chain_id), n_save, n_burn)
+    with cuda_handle(model, p, prior, priors, seed=99, n_chains=1, chain_offset=chain_id) as h:
+        got = h.run(n_burn, n_save)[0].T
+    assert got.shape == ref.shape
+    assert relnorm(got, ref) < 1e-7
+
+
+def test_chain_batching_and_modes_are_invariant():
+    """Draws of a chain id do not depend on batching, chain_offset or stats mode."""
+    from bsreg_b200 import capi
+    p = small_problem("sar", n=450, k=4)
+    with cuda_handle("sar", p, seed=5, n_chains=6) as h:
+        all6 = h.run(40, 30)
+    with cuda_handle("sar", p, seed=5, n_chains=2, chain_offset=3) as h:
+        part = h.run(40, 30)
+    assert np.array_equal(all6[3:5], part)
+    with cuda_handle("sar", p, seed=5, n_chains=6, stats_mode=capi.STATS_CACHED) as h:
+        cached = h.run(40, 30)
+    assert np.array_equal(all6, cached)
+
+
+def test_continue_and_state_roundtrip():
+    p = small_problem("sem", n=420, k=3)
+    with cuda_handle("sem", p, seed=8, n_chains=3) as h:
+        full = h.run(20, 40)
+    with cuda_handle("sem", p, seed=8, n_chains=3) as h:
+        a = h.run(20, 25)
+        st = h.get_state()
+        b = h.run(0, 15)                      # bm.bm continuation, R/60_interface.R:71-78
+        assert st["iterations"].tolist() == [45, 45, 45]
+    assert np.array_equal(np.concatenate([a, b], axis=2), full)
+    with cuda_handle("sem", p, seed=8, n_chains=3) as h2:
+        h2.set_state(st)
+        assert np.array_equal(h2.run(0, 15), b)
+
+
+def test_chebyshev_moments_and_nodes():
+    from bsreg_b200 import capi
+    p = small_problem("sar", n=800, k=3, symmetric=True)
+    order, probes, seed = 30, 32, 77
+    with cuda_handle("sar", p, ldet=capi.LDET_CHEBYSHEV, cheb_order=order, cheb_probes=probes, seed=seed) as h:
+        mom = h.eval_trace_moments(order, probes, seed)
+        want = core.trace_moments(p.W, order, probes, seed)
+        assert np.max(np.abs(mom - want)) / len(p.y) < 1e-12
+        re, im, w = h.nodes()
+        x, _, ww = core.chebyshev_nodes(want, len(p.y))
+        assert np.allclose(re, x, atol=1e-14) and np.allclose(w, ww, rtol=0, atol=1e-9 * len(p.y))
+        v = np.array([-0.5, 0.1, 0.6, 0.9])
+        got = h.eval_logdet(v)
+        same_input = np.array([core.ldet_nodes(t, re, im, w) for t in v])
+        assert np.max(np.abs(got - same_input) / np.maximum(np.abs(same_input), 1.0)) < 1e-8
+        exact = np.array([core.ldet_dense(t, p.W) for t in v])     # approximation error, reported separately
+        assert np.max(np.abs(got - exact)) < 0.05 * len(p.y) ** 0.5
