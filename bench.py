@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- SAR Gibbs chain-iterations/s at N = 100k, 64 chains per B200 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA arm
+    python bench.py --impl reference [...]                         CPU arm (oracle port of the R sampler)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+
+A "step" is one block of ITERS Gibbs iterations for all chains resident on a GPU
+(workload cfg4: synthetic SAR, N = 1e5, kNN(k=10) W, K = 20, 64 chains per GPU,
+Chebyshev log-determinant).  Chains are independent, so GPUs shard chains and
+never communicate inside the loop ("scaling": "weak", 64 chains per GPU).
+
+Prints ONE JSON line.  `value` is device-resident throughput (inputs already in
+HBM, draws left on the device); `e2e` is a complete fit through the C ABI from
+pinned HOST buffers: create (H2D of y, X, W + setup incl. the Chebyshev trace
+moments) + burn-in + sampling + D2H of the draws.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_OBS, K_REG, KNN, CHAINS_PER_GPU = 100_000, 20, 10, 64
+CHEB_ORDER, CHEB_PROBES = 50, 64
+ITERS_PER_STEP = 500
+E2E_BURN, E2E_SAVE = 500, 1000           # defaults of bm(), R/60_interface.R:39
+METRIC = "SAR Gibbs chain-iter/s at N=100k, 64 chains/GPU"
+
+
+def load_peaks():
+    try:
+        d = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_cfg4(n=N_OBS):
+    from bsreg_b200.synthetic import make_problem
+    return make_problem("sar", n=n, k_reg=K_REG, knn=KNN)
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference sampler, one chain per worker process
+# ----------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker(args):
+    chain_id, iters = args
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from oracle.sampler import NumpyRNG, RefChain
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    p, nodes = _W["p"], _W["nodes"]
+    ch = RefChain("sar", p.y, p.X, W=p.W, ldet=dict(kind="nodes", re=nodes[0], im=nodes[1], w=nodes[2]),
+                  rng=NumpyRNG(1000 + chain_id))
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        ch.sample()
+    return time.perf_counter() - t0
+
+
+def cpu_nodes(p):
+    from oracle import core
+    mom = core.trace_moments(p.W, 12, 8, 1)      # timing only: the node count (cost per log-det) is what matters
+    mom = np.concatenate([mom, np.zeros(CHEB_ORDER - 12)])
+    return core.chebyshev_nodes(mom, len(p.y))
+
+
+def cpu_throughput(p, nodes, iters, procs):
+    """chain-iter/s of `procs` independent oracle chains run in parallel processes."""
+    import multiprocessing as mp
+    _W["p"], _W["nodes"] = p, nodes
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(c, iters) for c in range(procs)])
+        wall = time.perf_counter() - t0
+    return procs * iters / wall, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    p = make_cfg4()
+    nodes = cpu_nodes(p)
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, CHAINS_PER_GPU))
+    iters = 40
+    for _ in range(args.warmup):
+        cpu_throughput(p, nodes, 5, procs)
+    t0 = time.perf_counter()
+    vals = [cpu_throughput(p, nodes, iters, procs)[0] for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    sample = f"{procs} chains x {iters} iterations per step, one single-threaded process per chain"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "chain-iter/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "chain-iter/s", "cores": procs, "kind": "port", "sample": sample,
+                         "note": "reference-algorithm CPU restatement (NumPy/SciPy), not R; R is not installed"},
+        "e2e": {"value": value, "unit": "chain-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n_gpus):
+    return {"workload": "cfg4: synthetic SAR, N=100000, kNN(k=10) row-stochastic W (nnz=1e6), K=20, "
+                        "Chebyshev log-det (order 50, 64 probes)",
+            "chains_per_gpu": CHAINS_PER_GPU, "global_chains": CHAINS_PER_GPU * n_gpus,
+            "iters_per_step": ITERS_PER_STEP, "parallelism": f"chains sharded over {n_gpus} GPU(s), no collective",
+            "stats_mode": "stream (W, y, X swept every iteration)",
+            "l2": "512 MiB L2 flush between timed steps; inside a step the 29 MB working set is L2-resident by "
+                  "construction of the Gibbs loop (same operands every iteration)"}
+
+
+# ----------------------------------------------------------------------------------------
+# CUDA arm
+# ----------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from bsreg_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the bsreg_b200 hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm_peak, peak_src = load_peaks()
+
+    p = make_cfg4()
+    n, k = p.X.shape
+    # pinned host copies of the inputs (column-major X as R would hand it over)
+    def pinned(a):
+        t = torch.empty(a.shape, dtype=torch.from_numpy(np.zeros(1, a.dtype)).dtype, pin_memory=True)
+        t.numpy()[...] = a
+        return t
+    ty, tXt = pinned(p.y), pinned(np.ascontiguousarray(p.X.T))
+    trp, tci, tva = pinned(p.W.indptr.astype(np.int32)), pinned(p.W.indices.astype(np.int32)), pinned(p.W.data)
+    import scipy.sparse as sp
+    Wp = sp.csr_matrix((tva.numpy(), tci.numpy(), trp.numpy()), shape=p.W.shape)
+    yp, Xp = ty.numpy(), tXt.numpy().T          # Xp is an F-ordered (n, k) view of pinned memory
+    h2d_bytes = yp.nbytes + Xp.nbytes + trp.numpy().nbytes + tci.numpy().nbytes + tva.numpy().nbytes
+
+    def create(seed=2024, stats=capi.STATS_STREAM):
+        return capi.Handle(yp, Xp, model=capi.MODEL_SAR, prior=capi.PRIOR_INDEPENDENT, W=Wp,
+                           ldet=capi.LDET_CHEBYSHEV, cheb_order=CHEB_ORDER, cheb_probes=CHEB_PROBES,
+                           stats_mode=stats, n_chains=CHAINS_PER_GPU, chain_offset=rank * CHAINS_PER_GPU, seed=seed)
+
+    h = create()
+    stream = torch.cuda.ExternalStream(h.stream())
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(handle, k_steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k_steps)]
+        for a, b in ev:
+            flush.zero_()
+            torch.cuda.synchronize()
+            a.record(stream)
+            handle.run_into(0, ITERS_PER_STEP, None, None)     # draws stay on the device
+            b.record(stream)
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in ev]
+
+    # ---- device-resident throughput ----
+    timed_steps(h, args.warmup)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = h.kernel_launches()
+    ms = timed_steps(h, args.steps)
+    launches = h.kernel_launches() - l0
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    total_ms = float(sum(ms))
+    if dist is not None:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    chain_iters = args.steps * ITERS_PER_STEP * CHAINS_PER_GPU * world
+    value = chain_iters / (total_ms * 1e-3)
+
+    # same loop with the sweep hoisted out (sufficient statistics cached at create)
+    hc = create(stats=capi.STATS_CACHED)
+    sc = torch.cuda.ExternalStream(hc.stream())
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hc.run_into(0, ITERS_PER_STEP, None, None)
+    torch.cuda.synchronize()
+    a.record(sc)
+    hc.run_into(0, 2 * ITERS_PER_STEP, None, None)
+    b.record(sc)
+    torch.cuda.synchronize()
+    cached_value = 2 * ITERS_PER_STEP * CHAINS_PER_GPU * world / (a.elapsed_time(b) * 1e-3)
+    hc.close()
+
+    # ---- kernel-level roofline for the dominant N-scale kernel (fused SpMM + Gram sweep) ----
+    def time_launches(fn, reps, cold):
+        if not cold:
+            fn(20)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); fn(reps); b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); fn(1); b.record(stream)
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / reps
+
+    roof = cpu = e2e = None
+    if rank == 0:
+        sweep_warm = time_launches(h.launch_sweep, 400, False)
+        sweep_cold = time_launches(h.launch_sweep, 20, True)
+        chain_ms = time_launches(h.launch_chain_step, 400, False)
+        bytes_sweep = h.sweep_bytes()
+        roof = {"kernel": "sweep_gram_kernel<6> (fused CSR SpMV + Gram reduction)", "bound": "hbm",
+                "achieved": bytes_sweep / (sweep_warm * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": bytes_sweep / (sweep_warm * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                "algorithmic_bytes": bytes_sweep, "peak_source": peak_src,
+                "launch_us": sweep_warm * 1e3,
+                "note": "in-loop condition: back-to-back launches, 29 MB working set L2-resident",
+                "cold": {"launch_us": sweep_cold * 1e3, "achieved": bytes_sweep / (sweep_cold * 1e-3) / 1e9,
+                         "frac": bytes_sweep / (sweep_cold * 1e-3) / 1e9 / hbm_peak,
+                         "note": "512 MiB L2 flush before every launch (operands come from HBM)"},
+                "chain_step_us": chain_ms * 1e3,
+                "share_of_iteration": sweep_warm / (sweep_warm + chain_ms)}
+    h.close()
+
+    # ---- end to end through the C ABI from pinned host buffers ----
+    draws_host = torch.empty((CHAINS_PER_GPU, k + 2, E2E_SAVE), dtype=torch.float64, pin_memory=True)
+    d2h_bytes = draws_host.numel() * 8
+
+    def one_fit(seed):
+        with create(seed=seed) as hh:
+            hh.run_into(E2E_BURN, E2E_SAVE, None, draws_host.data_ptr())
+
+    one_fit(1)
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        one_fit(100 + s)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = e2e_steps * (E2E_BURN + E2E_SAVE) * CHAINS_PER_GPU * world / e2e_s
+    lam_mean = float(draws_host.numpy()[:, -1, :].mean())
+
+    if rank == 0:
+        e2e = {"value": e2e_val, "unit": "chain-iter/s", "h2d_bytes_per_step": int(h2d_bytes),
+               "d2h_bytes_per_step": int(d2h_bytes), "ms_per_fit": 1e3 * e2e_s / e2e_steps,
+               "what": f"bsreg_create (H2D + setup + Chebyshev moments) + bsreg_run({E2E_BURN} burn, {E2E_SAVE} save) "
+                       "+ D2H of draws, per fit, wall clock incl. host work",
+               "posterior_mean_lambda": lam_mean}
+        # bounded CPU sample on this box's host cores
+        cores = os.cpu_count() or 1
+        procs = max(1, min(cores, CHAINS_PER_GPU))
+        cpu_val, cpu_wall = cpu_throughput(p, cpu_nodes(p), 40, procs)
+        cpu = {"value": cpu_val, "unit": "chain-iter/s", "cores": procs, "kind": "port",
+               "sample": f"{procs} chains x 40 iterations ({cpu_wall:.1f} s), one single-threaded process per chain",
+               "note": "reference-algorithm CPU restatement (NumPy/SciPy), not R; R is not installed"}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "chain-iter/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clk,
+            "cached_stats_value": cached_value,
+            "hbm_roofline_chain_iter_s": hbm_peak * 1e9 / h_bytes_per_chain_iter(bytes_sweep) * world,
+        }))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def h_bytes_per_chain_iter(bytes_sweep):
+    return bytes_sweep / CHAINS_PER_GPU
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

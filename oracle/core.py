@@ -37,10 +37,15 @@ def spmm(W: sp.csr_matrix, B: np.ndarray) -> np.ndarray:
 # ---------------------------------------------------------------------------
 # quadratic forms (K2)
 # ---------------------------------------------------------------------------
+def _sum(x) -> float:
+    """R's sum() accumulates in long double (R/00_aux.R:118); so does this."""
+    return float(np.sum(x, dtype=np.longdouble))
+
+
 def sq_sum(x) -> float:
-    """R/00_aux.R:117-119 (R's sum accumulates in long double; math.fsum is exact)."""
+    """R/00_aux.R:117-119."""
     x = np.asarray(x, dtype=np.float64).ravel()
-    return math.fsum(x * x)
+    return _sum(x * x)
 
 
 def residual_ss(y, X, Wy, WX, beta, lam, rho) -> float:
@@ -90,7 +95,7 @@ def ldet_nodes(lam: float, re, im, w) -> float:
     written on nodes: sum_k w_k * 0.5*log((1 - lam re_k)^2 + (lam im_k)^2)."""
     a = 1.0 - lam * np.asarray(re)
     b = lam * np.asarray(im)
-    return math.fsum(np.asarray(w) * 0.5 * np.log(a * a + b * b))
+    return _sum(np.asarray(w) * 0.5 * np.log(a * a + b * b))
 
 
 def ldet_dense(lam: float, W) -> float:
@@ -180,7 +185,7 @@ def sar_rss_coeffs(y, Wy, X, XX, sigma2, p0, mu0):
     b1 = chol_solve(A, p0 * mu0 + (X.T @ Wy) / sigma2)
     e0 = y - X @ b0
     e1 = Wy - X @ b1
-    return math.fsum(e0 * e0), math.fsum(e1 * e0), math.fsum(e1 * e1)
+    return _sum(e0 * e0), _sum(e1 * e0), _sum(e1 * e1)
 
 
 def sem_rss(v, y, Wy, X, WX):
