@@ -220,11 +220,30 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
 
   // ---- W (CSR) ----
   int *rp = nullptr, *ci = nullptr; double *va = nullptr;
+  dd.tile_rp = nullptr; dd.tile_maxnz = 0;
   if (p->nnz > 0 || h->model != BSREG_MODEL_LM || p->k_slx > 0) {
-    TRY(s.alloc(&rp, (size_t)n + 1)); TRY(s.alloc(&ci, (size_t)p->nnz)); TRY(s.alloc(&va, (size_t)p->nnz));
+    // padded so that the 16-byte staged copies of the sweep may over-read past the end
+    TRY(s.alloc(&rp, (size_t)n + 1 + 272)); TRY(s.alloc(&ci, (size_t)p->nnz + 8)); TRY(s.alloc(&va, (size_t)p->nnz + 4));
+    CU(cudaMemsetAsync(rp, 0, ((size_t)n + 1 + 272) * 4, s.stream));
+    CU(cudaMemsetAsync(ci, 0, ((size_t)p->nnz + 8) * 4, s.stream));
+    CU(cudaMemsetAsync(va, 0, ((size_t)p->nnz + 4) * 8, s.stream));
     TRY(upload(s, p->row_ptr, rp, ((size_t)n + 1) * 4));
     TRY(upload(s, p->col_idx, ci, (size_t)p->nnz * 4));
     TRY(upload(s, p->val, va, (size_t)p->nnz * 8));
+    const int R = sweep_tma_rows_per_tile(d);
+    if (R > 0 && h->model != BSREG_MODEL_LM) {   // row_ptr at tile boundaries for the staged sweep
+      const int ntiles = (n + R - 1) / R;
+      std::vector<int> trp(ntiles + 1);
+      int maxnz = 0;
+      for (int t = 0; t <= ntiles; ++t) trp[t] = p->row_ptr[std::min(t * R, n)];
+      for (int t = 0; t < ntiles; ++t) maxnz = std::max(maxnz, trp[t + 1] - trp[t]);
+      int *dtrp;
+      TRY(s.alloc(&dtrp, (size_t)ntiles + 1));
+      TRY(upload(s, trp.data(), dtrp, ((size_t)ntiles + 1) * 4));
+      CU(cudaStreamSynchronize(s.stream));
+      dd.tile_rp = dtrp;
+      dd.tile_maxnz = (maxnz + 3) & ~3;
+    }
   }
   dd.rp = rp; dd.ci = ci; dd.va = va;
 
@@ -257,6 +276,20 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   cudaFree(tmp);
   dd.y = y; dd.X = X;
   h->launches += 1;
+  // column-major, tile-padded copies for the TMA-staged sweep (LM / SAR, d <= 24)
+  dd.Xc = nullptr; dd.ypad = nullptr;
+  if (const int R = sweep_tma_rows_per_tile(d); R > 0 && h->model != BSREG_MODEL_SEM) {
+    const size_t ldx = (size_t)((n + R - 1) / R) * R;
+    double *xc, *yp;
+    TRY(s.alloc(&xc, ldx * m)); TRY(s.alloc(&yp, ldx));
+    CU(cudaMemsetAsync(xc, 0, ldx * m * 8, s.stream));
+    CU(cudaMemsetAsync(yp, 0, ldx * 8, s.stream));
+    launch_transpose(X, xc, m, n, (int)ldx, 0, s.stream);   // row-major [n][m] read as column-major m x n -> [m][ldx]
+    CU(cudaMemcpyAsync(yp, y, (size_t)n * 8, cudaMemcpyDeviceToDevice, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    dd.Xc = xc; dd.ypad = yp;
+    h->launches += 1;
+  }
 
   // ---- cached lags (R/15_sar.R:57, R/15_sem.R:63-64) ----
   dd.Wy = nullptr; dd.WX = nullptr;

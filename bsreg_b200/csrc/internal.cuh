@@ -20,12 +20,15 @@ struct DeviceData {
   const int *rp, *ci;
   const double *va;
   const double *y, *X;
+  const double *Xc, *ypad;    // TMA-staged sweep: X column-major with column stride ntiles*R (zero padded), y padded alike
   double *Wy, *WX;            // cached lags (R/15_sar.R:57, R/15_sem.R:63-64): direct-form kernel, generic sweep
   double *G;                  // d*d
   long long *Gfix;            // d*d, zero between sweeps
   const double *Gscale;       // d*d: value = Gfix * Gscale  (power of two)
   const double *Ginv_scale;   // d*d: fixed = rint(value * Ginv_scale)
   unsigned int *ticket;       // sweep completion counter
+  const int *tile_rp;         // row_ptr at tile boundaries for the staged sweep (null: not available)
+  int tile_maxnz;             // largest nonzero count of one tile
   // log-determinant nodes
   int n_nodes;
   const double *node_re, *node_im, *node_w;
@@ -68,6 +71,7 @@ void launch_spmm(int n, const int *rp, const int *ci, const double *va, const do
                  double *out, int ldo, int col0, double alpha, const double *C, double beta, cudaStream_t s);
 void launch_colnorms(const DeviceData &dd, double *norms, cudaStream_t s);
 bool sweep_fast_supported(const DeviceData &dd);
+int  sweep_tma_rows_per_tile(int d);   // rows per tile of the TMA-staged sweep, 0 if it does not cover this d
 void launch_sweep(const DeviceData &dd, int sm_count, cudaStream_t s);
 int  sweep_launch_count();
 void launch_residual_ss(const DeviceData &dd, int n_eval, const double *beta,

@@ -262,6 +262,224 @@ __global__ void __launch_bounds__(SweepCfg<NB>::T) sweep_gram_kernel(DeviceData 
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// K1 + K2 fused sweep, main path for d <= 24 (LM / SAR up to K = 22): TMA-staged.
+//
+// One persistent, warp-specialised CTA per SM around an S-stage shared-memory ring:
+//   producer warp : per tile of R rows, 1-D TMA bulk copies (cp.async.bulk, complete_tx on
+//                   an mbarrier) of the K column segments of X (X is kept COLUMN-major and
+//                   zero-padded to a whole number of tiles, so a tile column is one
+//                   contiguous R*8-byte run), of y, and of the tile's CSR slice
+//                   (row_ptr, col_idx, val).  Nothing N-scale passes through registers.
+//   gather warps  : spatial lag of the tile, Wy[r] = sum_p val[p] * y[col[p]] (CSR slice
+//                   from shared memory, y gathered from L2), written as column 1 of the tile.
+//   math warps    : lane = row, warp = one 6x6 block of G = Z'Z (diagonal blocks 21 DFMA,
+//                   off-diagonal 36 DFMA per row for 6 / 12 LDS.64); the column-major tile
+//                   makes every LDS conflict-free.  Blocks are dealt to warps so that the
+//                   four SM sub-partitions carry equal DFMA work.
+// full[s] / lag[s] / empty[s] mbarriers order producer -> gather -> math -> producer.
+// ---------------------------------------------------------------------------
+struct BlockMap { unsigned char gi[32], gj[32]; };
+
+template <int NG>
+struct S7 {
+  static constexpr int NBLK = NG * (NG + 1) / 2;
+  static constexpr int WPB = (NBLK >= 8) ? 1 : (NBLK >= 5 ? 2 : 4);   // math warps per block of G
+  static constexpr int MATH = NBLK * WPB;
+  static constexpr int GATHER = 4;
+  static constexpr int T = (MATH + GATHER + 1) * 32;                 // + producer warp
+  static constexpr int RPT = 4;                                       // rows per lane per tile
+  static constexpr int R = 32 * RPT;                                  // rows per tile
+  static constexpr int NC = 6 * NG;                                   // tile columns incl. zero padding
+  static constexpr int S = 4;                                         // ring stages
+};
+
+constexpr int S7_MAXNZ = 2560;   // nonzeros of one tile that fit the ring
+
+__host__ __device__ inline size_t s7_stage_doubles(int R, int NC, int maxnz) {
+  // Zt[NC][R] | VA[maxnz+4] | CI[maxnz+8] (ints) | RP[R+8] (ints); maxnz % 4 == 0 keeps 16-byte alignment
+  return (size_t)R * NC + (maxnz + 4) + (maxnz + 8) / 2 + (R + 8) / 2;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int NG>
+__global__ void __launch_bounds__(S7<NG>::T, 1)
+sweep_tma_kernel(DeviceData dd, int ntiles, const int *__restrict__ tile_rp, int maxnz, BlockMap bm) {
+  using C = S7<NG>;
+  constexpr int T = C::T, R = C::R, NC = C::NC, S = C::S, RPT = C::RPT, WPB = C::WPB, MATH = C::MATH, GATHER = C::GATHER;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) uint64_t full[S], lag[S], empty[S];
+  __shared__ int s_last;
+  const size_t stage_d = s7_stage_doubles(R, NC, maxnz);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int m = dd.m, d = dd.d;
+  const bool has_w = dd.model != 0;
+
+  auto stZ = [&](int s) { return smem + (size_t)s * stage_d; };
+  auto stVA = [&](int s) { return stZ(s) + (size_t)R * NC; };
+  auto stCI = [&](int s) { return reinterpret_cast<int *>(stVA(s) + maxnz + 4); };
+  auto stRP = [&](int s) { return stCI(s) + maxnz + 8; };
+
+  for (size_t e = tid; e < (size_t)S * stage_d; e += T) smem[e] = 0.0;   // padding columns stay zero
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&lag[s], GATHER); mbar_init(&empty[s], MATH); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic zero-fill before async-proxy writes
+
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const size_t ldx = (size_t)ntiles * R;                            // padded column stride of Xc / length of ypad
+
+  if (wid == MATH + GATHER) {
+    // =========================== producer ===========================
+    int p0 = 0, p1 = 0;
+    if (has_w && my_tiles > 0) { p0 = tile_rp[blockIdx.x]; p1 = tile_rp[blockIdx.x + 1]; }
+    for (int j = 0; j < my_tiles; ++j) {
+      const int s = j % S, tile = blockIdx.x + j * gridDim.x, r0 = tile * R;
+      int q0 = 0, q1 = 0;                                           // prefetch next tile's CSR range
+      if (has_w && j + 1 < my_tiles) { q0 = tile_rp[tile + gridDim.x]; q1 = tile_rp[tile + gridDim.x + 1]; }
+      mbar_wait(&empty[s], ((j / S) & 1) ^ 1);
+      const int a0 = p0 & ~3, b0 = p0 & ~1;
+      const uint32_t ci_bytes = has_w ? (uint32_t)((p1 - a0 + 3) / 4) * 16u : 0u;
+      const uint32_t va_bytes = has_w ? (uint32_t)((p1 - b0 + 1) / 2) * 16u : 0u;
+      const uint32_t rp_bytes = has_w ? (uint32_t)(R + 4) * 4u : 0u;
+      if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(m + 1) * R * 8u + ci_bytes + va_bytes + rp_bytes);
+      __syncwarp();
+      double *Z = stZ(s);
+      for (int c = lane; c < m; c += 32) tma_bulk_g2s(Z + (size_t)(2 + c) * R, dd.Xc + (size_t)c * ldx + r0, R * 8u, &full[s]);
+      if (lane == 31) tma_bulk_g2s(Z, dd.ypad + r0, R * 8u, &full[s]);
+      if (has_w) {
+        if (lane == 30) tma_bulk_g2s(stRP(s), dd.rp + r0, rp_bytes, &full[s]);
+        if (lane == 29 && ci_bytes) tma_bulk_g2s(stCI(s), dd.ci + a0, ci_bytes, &full[s]);
+        if (lane == 28 && va_bytes) tma_bulk_g2s(stVA(s), dd.va + b0, va_bytes, &full[s]);
+      }
+      p0 = q0; p1 = q1;
+    }
+  } else if (wid >= MATH) {
+    // =========================== gather: Wy of the tile ===========================
+    const int g = tid - MATH * 32;                                  // 0 .. 127
+    for (int j = 0; j < my_tiles; ++j) {
+      const int s = j % S, tile = blockIdx.x + j * gridDim.x, r0 = tile * R;
+      mbar_wait(&full[s], (j / S) & 1);
+      double *Z = stZ(s);
+      if (has_w) {
+        const int *RP = stRP(s), *CI = stCI(s);
+        const double *VA = stVA(s);
+        const int p0 = RP[0], a0 = p0 & ~3, b0 = p0 & ~1;
+        for (int r = g; r < R; r += GATHER * 32) {
+          double acc = 0.0;
+          if (r0 + r < dd.n) {
+            const int pb = RP[r], pe = RP[r + 1];
+            int p = pb;
+            for (; p + 4 <= pe; p += 4) {                           // four gathers in flight
+              const double y0 = dd.y[CI[p - a0]], y1 = dd.y[CI[p + 1 - a0]], y2 = dd.y[CI[p + 2 - a0]], y3 = dd.y[CI[p + 3 - a0]];
+              acc = fma(VA[p - b0], y0, acc); acc = fma(VA[p + 1 - b0], y1, acc);
+              acc = fma(VA[p + 2 - b0], y2, acc); acc = fma(VA[p + 3 - b0], y3, acc);
+            }
+            for (; p < pe; ++p) acc = fma(VA[p - b0], dd.y[CI[p - a0]], acc);
+          }
+          Z[R + r] = acc;                                           // column 1 = Wy
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&lag[s]);
+    }
+  } else {
+    // =========================== math: this warp's 6x6 block ===========================
+    const int blk = wid % C::NBLK, wr = wid / C::NBLK;
+    const int gi = bm.gi[blk], gj = bm.gj[blk];
+    const bool diag = gi == gj;
+    double acc[6][6];
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) acc[p][q] = 0.0;
+    for (int j = 0; j < my_tiles; ++j) {
+      const int s = j % S;
+      mbar_wait(&full[s], (j / S) & 1);
+      mbar_wait(&lag[s], (j / S) & 1);
+      const double *Z = stZ(s);
+#pragma unroll
+      for (int rr = 0; rr < RPT / WPB; ++rr) {
+        const int r = lane + 32 * (wr + WPB * rr);
+        double a[6], b[6];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) a[p] = Z[(6 * gi + p) * R + r];
+        if (diag) {
+#pragma unroll
+          for (int p = 0; p < 6; ++p)
+#pragma unroll
+            for (int q = p; q < 6; ++q) acc[p][q] = fma(a[p], a[q], acc[p][q]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < 6; ++p) b[p] = Z[(6 * gj + p) * R + r];
+#pragma unroll
+          for (int p = 0; p < 6; ++p)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc[p][q] = fma(a[p], b[q], acc[p][q]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    // lanes hold disjoint rows: fixed-order shuffle tree, then order-independent fixed-point atomics
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        if (diag && q < p) continue;
+        const double v = warp_sum(acc[p][q]);
+        const int ci_ = 6 * gi + p, cj_ = 6 * gj + q;
+        if (lane == 0 && ci_ < d && cj_ < d) {
+          const long long f = __double2ll_rn(v * dd.Ginv_scale[ci_ * d + cj_]);
+          atomicAdd(reinterpret_cast<unsigned long long *>(dd.Gfix + ci_ * d + cj_), (unsigned long long)f);
+        }
+      }
+  }
+  // ---- last CTA converts to double, mirrors, and re-zeroes the accumulators ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(dd.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int e = tid; e < d * d; e += T) {
+      const int i = e / d, j2 = e - i * d;
+      if (i <= j2) {
+        const long long f = __ldcg(dd.Gfix + e);
+        const double v = (double)f * dd.Gscale[e];
+        dd.G[i * d + j2] = v;
+        dd.G[j2 * d + i] = v;
+        dd.Gfix[e] = 0;
+      }
+    }
+    if (tid == 0) *dd.ticket = 0u;
+  }
+}
+
 // generic path (any d): one warp per entry of the upper triangle over materialised lags
 __global__ void gram_generic_kernel(DeviceData dd) {
   const int d = dd.d;
@@ -281,6 +499,50 @@ __global__ void gram_generic_kernel(DeviceData dd) {
 }
 
 bool sweep_fast_supported(const DeviceData &dd) { return dd.d <= 88; }
+
+int sweep_tma_rows_per_tile(int d) { return d <= 24 ? S7<4>::R : 0; }
+bool sweep_tma_supported(const DeviceData &dd) {
+  return dd.d <= 24 && dd.model != 2 && dd.Xc != nullptr && (dd.model == 0 || dd.tile_rp != nullptr) &&
+         dd.tile_maxnz <= S7_MAXNZ;
+}
+
+// deal the blocks of G to warps so that the four SM sub-partitions (warp % 4) carry equal DFMA work
+template <int NG>
+static BlockMap make_block_map() {
+  using C = S7<NG>;
+  BlockMap bm{};
+  int gi[32], gj[32], nb = 0;
+  for (int i = 0; i < NG; ++i) for (int j = i + 1; j < NG; ++j) { gi[nb] = i; gj[nb] = j; ++nb; }   // 36 FMAs per row
+  for (int i = 0; i < NG; ++i) { gi[nb] = i; gj[nb] = i; ++nb; }                                       // 21 FMAs per row
+  int load[4] = {0, 0, 0, 0}, used[32] = {0};
+  for (int b = 0; b < nb; ++b) {
+    int best = -1;
+    for (int w = 0; w < C::NBLK; ++w) {
+      if (used[w]) continue;
+      if (best < 0 || load[w % 4] < load[best % 4]) best = w;
+    }
+    used[best] = 1;
+    load[best % 4] += (gi[b] == gj[b]) ? 21 : 36;
+    bm.gi[best] = (unsigned char)gi[b];
+    bm.gj[best] = (unsigned char)gj[b];
+  }
+  return bm;
+}
+
+template <int NG>
+static void launch_sweep_tma(const DeviceData &dd, int sm_count, cudaStream_t s) {
+  using C = S7<NG>;
+  static BlockMap bm = make_block_map<NG>();
+  const size_t smem = (size_t)C::S * s7_stage_doubles(C::R, C::NC, dd.tile_maxnz) * sizeof(double);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(sweep_tma_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  const int ntiles = (dd.n + C::R - 1) / C::R;
+  const int grid = ntiles < sm_count ? ntiles : sm_count;
+  sweep_tma_kernel<NG><<<grid, C::T, smem, s>>>(dd, ntiles, dd.tile_rp, dd.tile_maxnz, bm);
+}
 
 template <int NB>
 static void launch_sweep_nb(const DeviceData &dd, int sm_count, cudaStream_t s) {
@@ -303,6 +565,13 @@ void launch_sweep(const DeviceData &dd, int sm_count, cudaStream_t s) {
     if (dd.model != 0) launch_spmm(dd.n, dd.rp, dd.ci, dd.va, dd.y, 1, 1, dd.Wy, 1, 0, 1.0, nullptr, 0.0, s);
     if (dd.model == 2) launch_spmm(dd.n, dd.rp, dd.ci, dd.va, dd.X, dd.m, dd.m, dd.WX, dd.m, 0, 1.0, nullptr, 0.0, s);
     gram_generic_kernel<<<296, 256, 0, s>>>(dd);
+    return;
+  }
+  if (sweep_tma_supported(dd)) {
+    if (dd.d <= 6) launch_sweep_tma<1>(dd, sm_count, s);
+    else if (dd.d <= 12) launch_sweep_tma<2>(dd, sm_count, s);
+    else if (dd.d <= 18) launch_sweep_tma<3>(dd, sm_count, s);
+    else launch_sweep_tma<4>(dd, sm_count, s);
     return;
   }
   const int nb = (dd.d + 3) / 4;
