@@ -1,0 +1,91 @@
+"""CUDA path through the PUBLIC interface (bsreg_b200.bm / blm / bsar / bsdem) on the real-data
+configs 1-3 of BASELINE.json, against the committed golden vectors and against the oracle."""
+import numpy as np
+import pytest
+
+import bsreg_b200 as bs
+from oracle import core
+from oracle.sampler import PhiloxRNG, RefChain, sample
+from tests.golden.make_golden import configs, design, load_cigarettes, panel_w
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cig():
+    return load_cigarettes()
+
+
+def _fit(cfg, seed, n_save, n_burn, **kw):
+    name, model, prior, pri, y, X, W, X_slx, reps = cfg
+    opts = bs.set_options(prior, SNG=bs.set_SNG(**pri["SNG"]) if "SNG" in pri else None)
+    ld = dict(reps=reps)
+    return bs.bm((y, X), type=model, W=W, options=opts, n_save=n_save, n_burn=n_burn, verbose=False, seed=seed,
+                 ldet_SAR=ld, ldet_SEM=ld, **kw)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_interface_reproduces_golden(cig, idx):
+    cfg = list(configs(cig))[idx]
+    g = np.load(f"tests/golden/golden_{cfg[0]}.npz")
+    fit = _fit(cfg, int(g["seed"]), int(g["n_save"]), int(g["n_burn"]))
+    assert fit.colnames == list(g["names"])
+    assert fit.draws.shape == g["draws"].shape
+    assert np.max(np.abs(fit.draws - g["draws"])) < 1e-7 * np.max(np.abs(g["draws"]))
+    G = fit.model.handle.eval_gram()
+    scale = np.sqrt(np.outer(np.diag(g["gram"]), np.diag(g["gram"])))
+    assert np.max(np.abs(G - g["gram"]) / scale) < 1e-12
+    if "ldet" in g:
+        got = fit.model.handle.eval_logdet(g["ldet_v"])
+        assert np.max(np.abs(got - g["ldet"])) < 1e-8 * max(1.0, np.max(np.abs(g["ldet"])))
+        st = fit.model.handle.get_state()
+        assert np.allclose([st["mh_scale"][0, 0], *st["mh_counters"][0, 0]], g["mh"])
+    assert "iterations" in fit.model.get_meta and str(fit).startswith("\nCall:")
+    assert set(fit.summary()) == set(fit.colnames)
+
+
+def test_continue_a_fit_like_bm_bm(cig):
+    """bm(x, n_save) on a `bm` object continues the chain and row-binds (R/60_interface.R:71-78)."""
+    cfg = list(configs(cig))[1]
+    a = _fit(cfg, 5, 30, 20)
+    b = bs.bm(a, n_save=15, verbose=False)
+    assert b.draws.shape == (45, a.draws.shape[1]) and np.array_equal(b.draws[:30], a.draws)
+    whole = _fit(cfg, 5, 45, 20)
+    assert np.max(np.abs(whole.draws - b.draws)) < 1e-9                 # same trajectory as an uninterrupted run
+    assert "65 iterations" in b.model.get_meta
+
+
+def test_multi_chain_object_and_chain_offset(cig):
+    cfg = list(configs(cig))[1]
+    fit = _fit(cfg, 9, 20, 20, n_chains=4)
+    assert fit.chains.shape == (4, 20, 5) and np.array_equal(fit.draws, fit.chains[0])
+    one = _fit(cfg, 9, 20, 20, n_chains=1, chain_offset=2)
+    assert np.array_equal(one.draws, fit.chains[2])                      # keyed by GLOBAL chain id
+    chains, names = fit.as_mcmc_list()
+    assert len(chains) == 4 and names[-1] == "lambda_SAR"
+
+
+@pytest.mark.parametrize("model", ["sar", "sem"])
+def test_paper_design_with_fixed_effects(cig, model):
+    """paper/1a_estimate_cont.R: M = 78 (state + year dummies).  Checks the on-chip K x K path at
+    large M and the Cholesky-based SEM rss against the oracle's Householder QR (cond^2 caveat)."""
+    y, X = design(cig, fixed_effects=True)
+    W = panel_w(cig)
+    assert X.shape == (1380, 3 + 45 + 29)
+    ch = RefChain(model, y, X, W=W, ldet=dict(kind="eigen", reps=30), rng=PhiloxRNG(3, 0))
+    ref = sample(ch, 10, 10)
+    fit = bs.bm((y, X), type=model, W=W, n_save=10, n_burn=10, verbose=False, seed=3,
+                ldet_SAR=dict(reps=30), ldet_SEM=dict(reps=30))
+    assert np.max(np.abs(fit.draws - ref)) < 1e-6 * np.max(np.abs(ref))
+    h = fit.model.handle
+    Wy, WX = core.spmm(ch.W, y), core.spmm(ch.W, X)
+    v = np.array([-0.5, 0.3, 0.9])
+    m = X.shape[1]
+    got = h.eval_conditionals(np.tile(ch.beta, (3, 1)), np.full(3, ch.sigma2), np.zeros(3), np.full((3, m), 1e-8), v)
+    for e in range(3):
+        if model == "sar":
+            c = core.sar_rss_coeffs(y, Wy, X, X.T @ X, ch.sigma2, np.full(m, 1e-8), np.zeros(m))
+            rss = c[0] - 2 * v[e] * c[1] + v[e] ** 2 * c[2]
+        else:
+            rss = core.sem_rss(v[e], y, Wy, X, WX)
+        assert abs(got["rss"][e] - rss) / rss < 1e-9
