@@ -42,14 +42,16 @@ int fail(int code, const char *fmt, ...) {
     if (r_ != BSREG_OK) return r_; \
   } while (0)
 
-constexpr int GRAPH_UNROLL = 20;      // Gibbs iterations per CUDA graph launch
+constexpr int GRAPH_UNROLL = 24;      // Gibbs iterations per CUDA graph launch (multiple of the 3 Gram buffers)
 constexpr int BLOCK_ITERS = 1000;     // iterations between host syncs / progress callbacks
 constexpr size_t DRAW_BUF_BYTES = (size_t)1 << 30;
 
 struct Shard {
   int dev = 0, sm_count = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, aux = nullptr;   // aux: chain-step branch of the iteration graph
   bool own_stream = false;
+  int64_t seq = 0;                    // index of the next sweep: it accumulates into Gram buffer seq % 3
+  std::vector<cudaEvent_t> events;
   int chain_lo = 0;                   // first chain of this shard inside the handle
   DeviceData dd{};
   ChainState cs{};
@@ -59,7 +61,7 @@ struct Shard {
   int save_cap = 0;
   double *p0_init = nullptr, *beta0 = nullptr;
   double *scratch = nullptr;          // partial sums for deterministic reductions
-  cudaGraphExec_t graph = nullptr;
+  cudaGraphExec_t graph = nullptr, sweep_graph = nullptr, chain_graph = nullptr;
 
   template <class T>
   int alloc(T **p, size_t count) {
@@ -91,21 +93,59 @@ int upload(Shard &s, const void *src, void *dst, size_t bytes) {
   return BSREG_OK;
 }
 
-// one Gibbs iteration = [fused sweep] + chain step
-int enqueue_iteration(bsreg_handle *h, Shard &s) {
-  if (h->stats_mode == BSREG_STATS_STREAM) { launch_sweep(s.dd, s.sm_count, s.stream); ++h->launches; }
-  launch_chain_step(s.dd, h->pr, s.cs, s.ctl_dev, s.draws_dev, s.stream);
+// Gram buffer rotation (internal.cuh): sweep j accumulates into buffer j % 3 and clears (j + 1) % 3
+void enqueue_sweep(bsreg_handle *h, Shard &s, cudaStream_t st) {
+  s.dd.gcur = (int)(s.seq % 3);
+  s.dd.gzero = (int)((s.seq + 1) % 3);
+  launch_sweep(s.dd, s.sm_count, st);
+  ++s.seq;
   ++h->launches;
+}
+
+void enqueue_chain_step(bsreg_handle *h, Shard &s, cudaStream_t st) {
+  s.dd.gcur = (int)((s.seq + 2) % 3);          // buffer of the latest sweep, (seq - 1) % 3
+  launch_chain_step(s.dd, h->pr, s.cs, s.ctl_dev, s.draws_dev, st);
+  ++h->launches;
+}
+
+// one Gibbs iteration = [fused sweep] + chain step, serialised on the shard's stream
+int enqueue_iteration(bsreg_handle *h, Shard &s) {
+  if (h->stats_mode == BSREG_STATS_STREAM) enqueue_sweep(h, s, s.stream);
+  enqueue_chain_step(h, s, s.stream);
   return BSREG_OK;
 }
 
+// GRAPH_UNROLL iterations as one CUDA graph.  The sweep does not depend on the chain state, so
+// inside the graph the sweeps (S) and the chain steps (C) form two chains with cross edges
+//   S_i <- S_{i-1}, C_{i-2}      (buffer (i + 1) % 3, cleared by S_i, was last read by C_{i-2})
+//   C_i <- C_{i-1}, S_i
+// and sweep i + 1 overlaps chain step i.
 int build_graph(bsreg_handle *h, Shard &s) {
   if (s.graph) return BSREG_OK;
+  const bool streamed = h->stats_mode == BSREG_STATS_STREAM;
+  if (s.events.empty()) {
+    s.events.resize(2 * GRAPH_UNROLL);
+    for (cudaEvent_t &e : s.events) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  cudaEvent_t *evS = s.events.data(), *evC = evS + GRAPH_UNROLL;
   cudaGraph_t g = nullptr;
+  const int64_t before = h->launches, seq0 = s.seq;
   CU(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
-  const int64_t before = h->launches;
-  for (int i = 0; i < GRAPH_UNROLL; ++i) enqueue_iteration(h, s);
+  for (int i = 0; i < GRAPH_UNROLL; ++i) {
+    if (streamed) {
+      if (i >= 2) CU(cudaStreamWaitEvent(s.stream, evC[i - 2], 0));
+      enqueue_sweep(h, s, s.stream);
+      CU(cudaEventRecord(evS[i], s.stream));
+      CU(cudaStreamWaitEvent(s.aux, evS[i], 0));
+      enqueue_chain_step(h, s, s.aux);
+      CU(cudaEventRecord(evC[i], s.aux));
+    } else {
+      enqueue_chain_step(h, s, s.stream);
+    }
+  }
+  if (streamed) CU(cudaStreamWaitEvent(s.stream, evC[GRAPH_UNROLL - 1], 0));
   h->launches = before;
+  s.seq = seq0;
   CU(cudaStreamEndCapture(s.stream, &g));
   CU(cudaGraphInstantiate(&s.graph, g, 0));
   CU(cudaGraphDestroy(g));
@@ -113,14 +153,49 @@ int build_graph(bsreg_handle *h, Shard &s) {
 }
 
 int enqueue_iterations(bsreg_handle *h, Shard &s, int count) {
-  const int per_iter = h->stats_mode == BSREG_STATS_STREAM ? 2 : 1;
-  if (count >= GRAPH_UNROLL) TRY(build_graph(h, s));
-  while (count >= GRAPH_UNROLL) {
-    CU(cudaGraphLaunch(s.graph, s.stream));
-    h->launches += (int64_t)GRAPH_UNROLL * per_iter;
-    count -= GRAPH_UNROLL;
+  const bool streamed = h->stats_mode == BSREG_STATS_STREAM;
+  const int per_iter = streamed ? 2 : 1;
+  while (count > 0) {
+    if (count >= GRAPH_UNROLL && (!streamed || s.seq % 3 == 0)) {
+      TRY(build_graph(h, s));
+      CU(cudaGraphLaunch(s.graph, s.stream));
+      h->launches += (int64_t)GRAPH_UNROLL * per_iter;
+      if (streamed) s.seq += GRAPH_UNROLL;
+      count -= GRAPH_UNROLL;
+    } else {
+      enqueue_iteration(h, s);
+      --count;
+    }
   }
-  for (; count > 0; --count) enqueue_iteration(h, s);
+  CU(cudaGetLastError());
+  return BSREG_OK;
+}
+
+// measurement helpers: reps back-to-back launches of one kernel, as graphs of GRAPH_UNROLL where possible
+int enqueue_repeated(bsreg_handle *h, Shard &s, int reps, bool sweep) {
+  cudaGraphExec_t &ge = sweep ? s.sweep_graph : s.chain_graph;
+  while (reps > 0) {
+    if (reps >= GRAPH_UNROLL && (!sweep || s.seq % 3 == 0)) {
+      if (!ge) {
+        cudaGraph_t g = nullptr;
+        const int64_t before = h->launches, seq0 = s.seq;
+        CU(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < GRAPH_UNROLL; ++i) { if (sweep) enqueue_sweep(h, s, s.stream); else enqueue_chain_step(h, s, s.stream); }
+        h->launches = before;
+        s.seq = seq0;
+        CU(cudaStreamEndCapture(s.stream, &g));
+        CU(cudaGraphInstantiate(&ge, g, 0));
+        CU(cudaGraphDestroy(g));
+      }
+      CU(cudaGraphLaunch(ge, s.stream));
+      h->launches += GRAPH_UNROLL;
+      if (sweep) s.seq += GRAPH_UNROLL;
+      reps -= GRAPH_UNROLL;
+    } else {
+      if (sweep) enqueue_sweep(h, s, s.stream); else enqueue_chain_step(h, s, s.stream);
+      --reps;
+    }
+  }
   CU(cudaGetLastError());
   return BSREG_OK;
 }
@@ -213,6 +288,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   s.sm_count = prop.multiProcessorCount;
   if (o->stream && h->shards.size() == 1) { s.stream = (cudaStream_t)o->stream; s.own_stream = false; }
   else { CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)); s.own_stream = true; }
+  CU(cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking));
   s.chain_lo = chain_lo;
   const int n = h->n, k = h->k, m = h->m, d = h->d;
   DeviceData &dd = s.dd;
@@ -220,7 +296,6 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
 
   // ---- W (CSR) ----
   int *rp = nullptr, *ci = nullptr; double *va = nullptr;
-  dd.tile_rp = nullptr; dd.tile_maxnz = 0;
   if (p->nnz > 0 || h->model != BSREG_MODEL_LM || p->k_slx > 0) {
     // padded so that the 16-byte staged copies of the sweep may over-read past the end
     TRY(s.alloc(&rp, (size_t)n + 1 + 272)); TRY(s.alloc(&ci, (size_t)p->nnz + 8)); TRY(s.alloc(&va, (size_t)p->nnz + 4));
@@ -230,20 +305,6 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
     TRY(upload(s, p->row_ptr, rp, ((size_t)n + 1) * 4));
     TRY(upload(s, p->col_idx, ci, (size_t)p->nnz * 4));
     TRY(upload(s, p->val, va, (size_t)p->nnz * 8));
-    const int R = sweep_tma_rows_per_tile(d);
-    if (R > 0 && h->model != BSREG_MODEL_LM) {   // row_ptr at tile boundaries for the staged sweep
-      const int ntiles = (n + R - 1) / R;
-      std::vector<int> trp(ntiles + 1);
-      int maxnz = 0;
-      for (int t = 0; t <= ntiles; ++t) trp[t] = p->row_ptr[std::min(t * R, n)];
-      for (int t = 0; t < ntiles; ++t) maxnz = std::max(maxnz, trp[t + 1] - trp[t]);
-      int *dtrp;
-      TRY(s.alloc(&dtrp, (size_t)ntiles + 1));
-      TRY(upload(s, trp.data(), dtrp, ((size_t)ntiles + 1) * 4));
-      CU(cudaStreamSynchronize(s.stream));
-      dd.tile_rp = dtrp;
-      dd.tile_maxnz = (maxnz + 3) & ~3;
-    }
   }
   dd.rp = rp; dd.ci = ci; dd.va = va;
 
@@ -276,19 +337,49 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   cudaFree(tmp);
   dd.y = y; dd.X = X;
   h->launches += 1;
-  // column-major, tile-padded copies for the TMA-staged sweep (LM / SAR, d <= 24)
-  dd.Xc = nullptr; dd.ypad = nullptr;
-  if (const int R = sweep_tma_rows_per_tile(d); R > 0 && h->model != BSREG_MODEL_SEM) {
-    const size_t ldx = (size_t)((n + R - 1) / R) * R;
-    double *xc, *yp;
-    TRY(s.alloc(&xc, ldx * m)); TRY(s.alloc(&yp, ldx));
-    CU(cudaMemsetAsync(xc, 0, ldx * m * 8, s.stream));
-    CU(cudaMemsetAsync(yp, 0, ldx * 8, s.stream));
-    launch_transpose(X, xc, m, n, (int)ldx, 0, s.stream);   // row-major [n][m] read as column-major m x n -> [m][ldx]
-    CU(cudaMemcpyAsync(yp, y, (size_t)n * 8, cudaMemcpyDeviceToDevice, s.stream));
-    CU(cudaStreamSynchronize(s.stream));
-    dd.Xc = xc; dd.ypad = yp;
-    h->launches += 1;
+  // ---- tile-blocked operands of the ring sweep (sweep.cu): Zt and the per-tile CSR blobs ----
+  dd.Zt = nullptr; dd.csr_blob = nullptr; dd.tile_off = nullptr; dd.tile_max_blob = 0;
+  {
+    constexpr int R = SWEEP_TILE_ROWS;
+    const int ntiles = (n + R - 1) / R;
+    std::vector<long long> off(ntiles + 1, 0);
+    std::vector<unsigned char> blob;
+    int max_blob = 0;
+    const bool with_w = h->model != BSREG_MODEL_LM;
+    if (with_w) {
+      for (int t = 0; t < ntiles; ++t) {
+        const int r0 = t * R, p0 = p->row_ptr[r0];
+        const int nz = p->row_ptr[std::min(r0 + R, n)] - p0;
+        off[t + 1] = off[t] + (R + 4) * 4 + (long long)((nz + 1) & ~1) * 8 + (long long)((nz + 3) & ~3) * 4;
+        max_blob = std::max<long long>(max_blob, off[t + 1] - off[t]);
+      }
+    }
+    if (sweep_ring_supported(d, h->model, max_blob)) {
+      double *zt;
+      TRY(s.alloc(&zt, (size_t)ntiles * (m + 1) * R));
+      launch_pack_tiles(X, y, zt, n, m, s.stream);
+      h->launches += 1;
+      dd.Zt = zt;
+      if (with_w) {
+        blob.assign((size_t)off[ntiles], 0);
+        for (int t = 0; t < ntiles; ++t) {
+          const int r0 = t * R, p0 = p->row_ptr[r0];
+          int *rpl = reinterpret_cast<int *>(blob.data() + off[t]);
+          for (int i = 0; i <= R; ++i) rpl[i] = p->row_ptr[std::min(r0 + i, n)] - p0;
+          const int nz = rpl[R];
+          double *bva = reinterpret_cast<double *>(blob.data() + off[t] + (R + 4) * 4);
+          int *bci = reinterpret_cast<int *>(bva + ((nz + 1) & ~1));
+          std::copy(p->val + p0, p->val + p0 + nz, bva);
+          std::copy(p->col_idx + p0, p->col_idx + p0 + nz, bci);
+        }
+        unsigned char *db; long long *doff;
+        TRY(s.alloc(&db, blob.size() + 16)); TRY(s.alloc(&doff, (size_t)ntiles + 1));
+        TRY(upload(s, blob.data(), db, blob.size()));
+        TRY(upload(s, off.data(), doff, ((size_t)ntiles + 1) * 8));
+        CU(cudaStreamSynchronize(s.stream));
+        dd.csr_blob = db; dd.tile_off = doff; dd.tile_max_blob = max_blob;
+      }
+    }
   }
 
   // ---- cached lags (R/15_sar.R:57, R/15_sem.R:63-64) ----
@@ -306,11 +397,10 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
 
   // ---- Gram accumulators and fixed-point scales ----
   double *norms, *gscale, *ginv;
-  TRY(s.alloc(&dd.G, (size_t)d * d)); TRY(s.alloc(&dd.Gfix, (size_t)d * d)); TRY(s.alloc(&dd.ticket, 1));
+  TRY(s.alloc(&dd.Gfix, (size_t)3 * d * d));
   TRY(s.alloc(&norms, (size_t)d)); TRY(s.alloc(&gscale, (size_t)d * d)); TRY(s.alloc(&ginv, (size_t)d * d));
   TRY(s.alloc(&s.scratch, 4096));
-  CU(cudaMemsetAsync(dd.Gfix, 0, (size_t)d * d * 8, s.stream));
-  CU(cudaMemsetAsync(dd.ticket, 0, 4, s.stream));
+  CU(cudaMemsetAsync(dd.Gfix, 0, (size_t)3 * d * d * 8, s.stream));
   launch_colnorms(dd, norms, s.stream);
   ++h->launches;
   std::vector<double> hn(d), hs((size_t)d * d), hi((size_t)d * d);
@@ -328,8 +418,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   TRY(upload(s, hi.data(), ginv, (size_t)d * d * 8));
   CU(cudaStreamSynchronize(s.stream));
   dd.Gscale = gscale; dd.Ginv_scale = ginv;
-  launch_sweep(dd, s.sm_count, s.stream);
-  ++h->launches;
+  enqueue_sweep(h, s, s.stream);
 
   // ---- chain state ----
   ChainState &cs = s.cs;
@@ -362,6 +451,7 @@ int init_chains(bsreg_handle *h, bool refresh_only) {
     CU(cudaSetDevice(s.dev));
     ChainInit ci{s.beta0, o.ng_sigma0, o.sp_lambda, o.sp_lambda_scale, o.hs_lambda, o.hs_tau, o.hs_zeta, o.hs_nu,
                  o.sng_lambda, o.sng_tau, o.sng_theta, o.sng_theta_scale, s.p0_init, refresh_only};
+    s.dd.gcur = (int)((s.seq + 2) % 3);
     launch_chain_init(s.dd, h->pr, s.cs, ci, s.stream);
     ++h->launches;
     CU(cudaGetLastError());
@@ -466,7 +556,12 @@ void bsreg_destroy(bsreg_handle *h) {
   for (Shard &s : h->shards) {
     cudaSetDevice(s.dev);
     if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.aux) cudaStreamSynchronize(s.aux);
     if (s.graph) cudaGraphExecDestroy(s.graph);
+    if (s.sweep_graph) cudaGraphExecDestroy(s.sweep_graph);
+    if (s.chain_graph) cudaGraphExecDestroy(s.chain_graph);
+    for (cudaEvent_t e : s.events) cudaEventDestroy(e);
+    if (s.aux) cudaStreamDestroy(s.aux);
     for (void *q : s.allocs) cudaFree(q);
     if (s.draws_dev) cudaFree(s.draws_dev);
     if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
@@ -501,7 +596,8 @@ int bsreg_run(bsreg_handle *h, int32_t n_burn, int32_t n_save, const bsreg_mh *m
     int cap = (int)std::min<size_t>((size_t)std::max(n_save, 1), std::max<size_t>(DRAW_BUF_BYTES / row_bytes, 1));
     if (cap > s.save_cap) {
       CU(cudaStreamSynchronize(s.stream));
-      if (s.graph) { cudaGraphExecDestroy(s.graph); s.graph = nullptr; }   // the graph bakes the buffer pointer
+      if (s.graph) { cudaGraphExecDestroy(s.graph); s.graph = nullptr; }   // the graphs bake the buffer pointer
+      if (s.chain_graph) { cudaGraphExecDestroy(s.chain_graph); s.chain_graph = nullptr; }
       if (s.draws_dev) cudaFree(s.draws_dev);
       s.draws_dev = nullptr;
       CU(cudaMalloc(&s.draws_dev, (size_t)cap * row_bytes));
@@ -661,11 +757,16 @@ int bsreg_eval_gram(bsreg_handle *h, double *G) {
   if (!h || !G) return fail(BSREG_EINVAL, "bad argument");
   Shard &s = h->shards[0];
   CU(cudaSetDevice(s.dev));
-  launch_sweep(s.dd, s.sm_count, s.stream);
+  enqueue_sweep(h, s, s.stream);
+  double *dG;
+  CU(cudaMalloc(&dG, (size_t)h->d * h->d * 8));
+  s.dd.gcur = (int)((s.seq + 2) % 3);
+  launch_gram_to_double(s.dd, dG, s.stream);
   ++h->launches;
   CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(G, s.dd.G, (size_t)h->d * h->d * 8, cudaMemcpyDeviceToHost, s.stream));
+  CU(cudaMemcpyAsync(G, dG, (size_t)h->d * h->d * 8, cudaMemcpyDeviceToHost, s.stream));
   CU(cudaStreamSynchronize(s.stream));
+  cudaFree(dG);
   return BSREG_OK;
 }
 
@@ -747,6 +848,7 @@ int bsreg_eval_conditionals(bsreg_handle *h, int32_t n_eval, const double *beta,
   CU(cudaMemcpyAsync(ds2, sigma2, ne * 8, cudaMemcpyHostToDevice, s.stream));
   CU(cudaMemcpyAsync(dl, lam, ne * 8, cudaMemcpyHostToDevice, s.stream));
   CU(cudaMemcpyAsync(dv, v, ne * 8, cudaMemcpyHostToDevice, s.stream));
+  s.dd.gcur = (int)((s.seq + 2) % 3);
   launch_eval_conditionals(s.dd, h->pr, s.cs.mu0, n_eval, db, ds2, dl, dp0, dv, dmu1, drate, drss, dlp, s.stream);
   ++h->launches;
   CU(cudaGetLastError());
@@ -784,10 +886,7 @@ int bsreg_launch_sweep(bsreg_handle *h, int32_t reps) {
   if (!h) return fail(BSREG_EINVAL, "null handle");
   Shard &s = h->shards[0];
   CU(cudaSetDevice(s.dev));
-  for (int i = 0; i < reps; ++i) launch_sweep(s.dd, s.sm_count, s.stream);
-  h->launches += reps;
-  CU(cudaGetLastError());
-  return BSREG_OK;
+  return enqueue_repeated(h, s, reps, true);
 }
 
 int bsreg_launch_chain_step(bsreg_handle *h, int32_t reps) {
@@ -797,10 +896,7 @@ int bsreg_launch_chain_step(bsreg_handle *h, int32_t reps) {
   RunCtl ctl{};
   ctl.n_burn = 1 << 30; ctl.tune_limit = 0; ctl.store = 0; ctl.acc_lo = 0.2; ctl.acc_hi = 0.45; ctl.acc_change = 0.8;
   CU(cudaMemcpyAsync(s.ctl_dev, &ctl, sizeof ctl, cudaMemcpyHostToDevice, s.stream));
-  for (int i = 0; i < reps; ++i) launch_chain_step(s.dd, h->pr, s.cs, s.ctl_dev, s.draws_dev, s.stream);
-  h->launches += reps;
-  CU(cudaGetLastError());
-  return BSREG_OK;
+  return enqueue_repeated(h, s, reps, false);
 }
 
 int bsreg_sync(bsreg_handle *h) {

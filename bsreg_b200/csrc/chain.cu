@@ -46,19 +46,28 @@ __device__ __forceinline__ double bsum(double v, double *red) {
 }
 
 // ---- views of the Gram matrix G (d x d, symmetric), Z = [y | Wy | X | WX] ----
+// Small designs stage the whole matrix in shared memory at kernel start (Gs != null); wide ones
+// (d*d beyond the budget) read the fixed-point buffer through L2 on demand.
 struct GView {
-  const double *G;
+  const double *Gs;
+  const long long *Gfix;       // this launch's fixed-point buffer
+  const double *Gscale;
   int d, m, model;
-  __device__ __forceinline__ double yy() const { return G[0]; }
-  __device__ __forceinline__ double yWy() const { return G[1]; }
-  __device__ __forceinline__ double WyWy() const { return G[d + 1]; }
-  __device__ __forceinline__ double Xy(int a) const { return G[2 + a]; }
-  __device__ __forceinline__ double XWy(int a) const { return G[d + 2 + a]; }
-  __device__ __forceinline__ double XX(int a, int b) const { return G[(2 + a) * d + 2 + b]; }
-  __device__ __forceinline__ double WXy(int a) const { return G[2 + m + a]; }
-  __device__ __forceinline__ double WXWy(int a) const { return G[d + 2 + m + a]; }
-  __device__ __forceinline__ double XWX(int a, int b) const { return G[(2 + a) * d + 2 + m + b]; }
-  __device__ __forceinline__ double WXWX(int a, int b) const { return G[(2 + m + a) * d + 2 + m + b]; }
+  __device__ __forceinline__ double at(int i, int j) const {
+    if (Gs) return Gs[i * d + j];
+    const int e = i <= j ? i * d + j : j * d + i;
+    return (double)Gfix[e] * Gscale[e];
+  }
+  __device__ __forceinline__ double yy() const { return at(0, 0); }
+  __device__ __forceinline__ double yWy() const { return at(0, 1); }
+  __device__ __forceinline__ double WyWy() const { return at(1, 1); }
+  __device__ __forceinline__ double Xy(int a) const { return at(0, 2 + a); }
+  __device__ __forceinline__ double XWy(int a) const { return at(1, 2 + a); }
+  __device__ __forceinline__ double XX(int a, int b) const { return at(2 + a, 2 + b); }
+  __device__ __forceinline__ double WXy(int a) const { return at(0, 2 + m + a); }
+  __device__ __forceinline__ double WXWy(int a) const { return at(1, 2 + m + a); }
+  __device__ __forceinline__ double XWX(int a, int b) const { return at(2 + a, 2 + m + b); }
+  __device__ __forceinline__ double WXWX(int a, int b) const { return at(2 + m + a, 2 + m + b); }
   // working quantities at lambda: R/15_sar.R:132-133 (z, X'z), R/15_sem.R:28-36 (filtered y, X)
   __device__ __forceinline__ double xx_eff(int a, int b, double l) const {
     if (model != 2) return XX(a, b);
@@ -141,22 +150,35 @@ __device__ __forceinline__ double logpost_lambda(double v, double ldet, double r
 
 // shared-memory workspace of one chain
 struct Work {
-  double *T, *dg, *p0, *mu0, *beta, *mu1, *b0, *b1, *eps, *t0, *t1, *red;
+  double *T, *dg, *p0, *mu0, *beta, *mu1, *b0, *b1, *eps, *t0, *t1, *red, *G;
 };
 
+constexpr int G_STAGE_MAX_D = 48;     // stage G in shared memory up to this Gram dimension (18 KB)
+__host__ __device__ inline int gram_dim(int m, int model) { return model == 2 ? 2 * m + 2 : m + 2; }
+__host__ __device__ inline bool g_staged(int m, int model) { return gram_dim(m, model) <= G_STAGE_MAX_D; }
 __host__ __device__ inline int work_ld(int m) { return m | 1; }
-__host__ __device__ inline size_t work_doubles(int m) {
-  return (size_t)(2 * m + 3) * work_ld(m) + 10 * (size_t)m + 16;
+__host__ __device__ inline size_t work_doubles(int m, int model) {
+  const size_t d = gram_dim(m, model);
+  return (size_t)(2 * m + 3) * work_ld(m) + 10 * (size_t)m + 16 + (g_staged(m, model) ? d * d : 0);
 }
 
-__device__ __forceinline__ Work carve(double *sm, int m) {
+__device__ __forceinline__ Work carve(double *sm, int m, int model) {
   Work w;
   w.T = sm;
   w.dg = w.T + (size_t)(2 * m + 3) * work_ld(m);
   w.p0 = w.dg + m; w.mu0 = w.p0 + m; w.beta = w.mu0 + m; w.mu1 = w.beta + m;
   w.b0 = w.mu1 + m; w.b1 = w.b0 + m; w.eps = w.b1 + m; w.t0 = w.eps + m; w.t1 = w.t0 + m;
   w.red = w.t1 + m;
+  w.G = g_staged(m, model) ? w.red + 16 : nullptr;
   return w;
+}
+
+// copy the Gram matrix of this launch's buffer into shared memory (both triangles)
+template <int NT>
+__device__ __forceinline__ void stage_gram(const DeviceData &dd, double *Gs) {
+  if (Gs == nullptr) return;
+  const int d = dd.d;
+  for (int e = threadIdx.x; e < d * d; e += NT) Gs[e] = g_load(dd, e / d, e - (e / d) * d);
 }
 
 // || y* - X* b ||^2 = y*'y* - 2 b'X*'y* + b'X*'X* b   (R/10_lm.R:176 via R/10_lm.R:192)
@@ -266,8 +288,9 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
   extern __shared__ double sm[];
   const int c = blockIdx.x, tid = threadIdx.x, m = dd.m, n = dd.n;
   const int A = aux_len(m), ld = work_ld(m);
-  Work w = carve(sm, m);
-  const GView g{dd.G, dd.d, m, dd.model};
+  Work w = carve(sm, m, dd.model);
+  stage_gram<NT>(dd, w.G);
+  const GView g{w.G, dd.Gfix + (size_t)dd.gcur * dd.d * dd.d, dd.Gscale, dd.d, m, dd.model};
   const bool conj = pr.prior == 1, hs = pr.prior == 3, sng = pr.prior == 2;
   const bool sar = dd.model == 1, sem = dd.model == 2;
   double *aux = cs.aux + (size_t)c * A;
@@ -500,7 +523,7 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
   }
 }
 
-size_t chain_smem_bytes(int m, int, int) { return work_doubles(m) * sizeof(double); }
+size_t chain_smem_bytes(int m, int model, int) { return work_doubles(m, model) * sizeof(double); }
 int chain_threads(int m) { return m <= 32 ? 32 : 128; }
 
 template <int NT>
@@ -553,8 +576,9 @@ __global__ void __launch_bounds__(NT) eval_cond_kernel(DeviceData dd, Priors pr,
                                                        double *logpost) {
   extern __shared__ double sm[];
   const int e = blockIdx.x, tid = threadIdx.x, m = dd.m, ld = work_ld(m);
-  Work w = carve(sm, m);
-  const GView g{dd.G, dd.d, m, dd.model};
+  Work w = carve(sm, m, dd.model);
+  stage_gram<NT>(dd, w.G);
+  const GView g{w.G, dd.Gfix + (size_t)dd.gcur * dd.d * dd.d, dd.Gscale, dd.d, m, dd.model};
   const bool conj = pr.prior == 1;
   for (int a = tid; a < m; a += NT) {
     w.mu0[a] = mu0[a]; w.p0[a] = p0[(size_t)e * m + a]; w.beta[a] = beta[(size_t)e * m + a];

@@ -10,29 +10,41 @@ namespace bsreg {
 //   X     row-major [n][m]   (m includes SLX-lagged columns)
 //   y     [n]
 //   W     CSR: rp int32 [n+1], ci int32 [nnz], va f64 [nnz]
-//   G     f64 [d][d] symmetric Gram of Z = [y | Wy | X | WX]
-//         d = m + 2 (LM: Wy column is zero; SAR) or 2m + 2 (SEM)
-//   Gfix  int64 fixed-point accumulators behind G (order-independent atomics)
+//   G     symmetric Gram of Z = [y | Wy | X | WX], d = m + 2 (LM: Wy column is zero; SAR) or 2m + 2 (SEM),
+//         held ONLY as int64 fixed-point accumulators Gfix[3][d][d] (upper triangle; integer
+//         atomics make the sum independent of CTA order).  Sweep j accumulates into buffer
+//         j % 3 and clears buffer (j + 1) % 3; the chain step of iteration j reads buffer j % 3,
+//         so sweep j + 1 can overlap chain step j.  value = Gfix * Gscale (power of two).
+//   Zt    ring sweep: [ntiles][m+1][R] tile-blocked copy of [X | y] (column-major inside a tile)
+//   csr_blob / tile_off: per tile {int rp_local[R+4]; double va[nz~2]; int ci[nz~4]}, 16-byte aligned
 // ---------------------------------------------------------------------------
+constexpr int SWEEP_TILE_ROWS = 64;
+
 struct DeviceData {
   int n, m, d, model;
   int64_t nnz;
   const int *rp, *ci;
   const double *va;
   const double *y, *X;
-  const double *Xc, *ypad;    // TMA-staged sweep: X column-major with column stride ntiles*R (zero padded), y padded alike
+  const double *Zt;           // ring sweep: tile-blocked [X | y] (null: design not covered by the ring)
+  const unsigned char *csr_blob;
+  const long long *tile_off;  // ntiles + 1 byte offsets into csr_blob
+  int tile_max_blob;          // largest blob of one tile (bytes)
   double *Wy, *WX;            // cached lags (R/15_sar.R:57, R/15_sem.R:63-64): direct-form kernel, generic sweep
-  double *G;                  // d*d
-  long long *Gfix;            // d*d, zero between sweeps
+  long long *Gfix;            // 3 * d*d
+  int gcur, gzero;            // buffer this launch accumulates into / reads; buffer a sweep clears (-1: none)
   const double *Gscale;       // d*d: value = Gfix * Gscale  (power of two)
   const double *Ginv_scale;   // d*d: fixed = rint(value * Ginv_scale)
-  unsigned int *ticket;       // sweep completion counter
-  const int *tile_rp;         // row_ptr at tile boundaries for the staged sweep (null: not available)
-  int tile_maxnz;             // largest nonzero count of one tile
   // log-determinant nodes
   int n_nodes;
   const double *node_re, *node_im, *node_w;
 };
+
+// entry (i, j) of the Gram matrix from the fixed-point buffer of this launch
+__device__ __forceinline__ double g_load(const DeviceData &dd, int i, int j) {
+  const int e = i <= j ? i * dd.d + j : j * dd.d + i;
+  return (double)dd.Gfix[(size_t)dd.gcur * dd.d * dd.d + e] * dd.Gscale[e];
+}
 
 struct Priors {
   int prior;
@@ -71,7 +83,9 @@ void launch_spmm(int n, const int *rp, const int *ci, const double *va, const do
                  double *out, int ldo, int col0, double alpha, const double *C, double beta, cudaStream_t s);
 void launch_colnorms(const DeviceData &dd, double *norms, cudaStream_t s);
 bool sweep_fast_supported(const DeviceData &dd);
-int  sweep_tma_rows_per_tile(int d);   // rows per tile of the TMA-staged sweep, 0 if it does not cover this d
+bool sweep_ring_supported(int d, int model, int max_blob);   // does the TMA-fed ring sweep cover this design
+void launch_pack_tiles(const double *X, const double *y, double *Zt, int n, int m, cudaStream_t s);
+void launch_gram_to_double(const DeviceData &dd, double *G, cudaStream_t s);
 void launch_sweep(const DeviceData &dd, int sm_count, cudaStream_t s);
 int  sweep_launch_count();
 void launch_residual_ss(const DeviceData &dd, int n_eval, const double *beta,

@@ -13,6 +13,8 @@
 // All reductions are bit-reproducible: fixed-order trees inside a CTA, and 64-bit
 // fixed-point integer atomics across CTAs (integer addition is associative, so the
 // result does not depend on CTA arrival order).
+#include <cstdlib>
+
 #include "internal.cuh"
 #include "rng.cuh"
 
@@ -47,6 +49,37 @@ __global__ void transpose_kernel(const double *__restrict__ src, double *__restr
 void launch_transpose(const double *src, double *dst, int n, int m, int ld, int col0, cudaStream_t s) {
   dim3 grid((n + 31) / 32, (m + 31) / 32), block(32, 8);
   transpose_kernel<<<grid, block, 0, s>>>(src, dst, n, m, ld, col0);
+}
+
+// Zt[tile][c][r] for the ring sweep: columns X_1..X_m then y, zero padded to whole tiles
+__global__ void pack_tiles_kernel(const double *__restrict__ X, const double *__restrict__ y, double *__restrict__ Zt,
+                                  int n, int m, int ntiles) {
+  constexpr int R = SWEEP_TILE_ROWS;
+  const size_t total = (size_t)ntiles * (m + 1) * R;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx % R);
+    const size_t tc = idx / R;
+    const int c = (int)(tc % (m + 1)), tile = (int)(tc / (m + 1));
+    const int row = tile * R + r;
+    double v = 0.0;
+    if (row < n) v = c < m ? X[(size_t)row * m + c] : y[row];
+    Zt[idx] = v;
+  }
+}
+
+void launch_pack_tiles(const double *X, const double *y, double *Zt, int n, int m, cudaStream_t s) {
+  const int ntiles = (n + SWEEP_TILE_ROWS - 1) / SWEEP_TILE_ROWS;
+  pack_tiles_kernel<<<592, 256, 0, s>>>(X, y, Zt, n, m, ntiles);
+}
+
+// fixed-point accumulator -> symmetric double matrix (parity entry point bsreg_eval_gram)
+__global__ void gram_to_double_kernel(DeviceData dd, double *G) {
+  const int d = dd.d;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < d * d; e += gridDim.x * blockDim.x) G[e] = g_load(dd, e / d, e % d);
+}
+
+void launch_gram_to_double(const DeviceData &dd, double *G, cudaStream_t s) {
+  gram_to_double_kernel<<<(dd.d * dd.d + 255) / 256, 256, 0, s>>>(dd, G);
 }
 
 // ---------------------------------------------------------------------------
@@ -133,11 +166,14 @@ __global__ void __launch_bounds__(SweepCfg<NB>::T) sweep_gram_kernel(DeviceData 
   using Cfg = SweepCfg<NB>;
   constexpr int B = Cfg::B, RG = Cfg::RG, T = Cfg::T, RPT = Cfg::RPT, R = Cfg::R, DP = Cfg::DP;
   __shared__ __align__(16) double Z[R * DP];
-  __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int m = dd.m, d = dd.d, n = dd.n;
   const bool sem = dd.model == 2, has_w = dd.model != 0;
+  if (blockIdx.x == 0 && dd.gzero >= 0) {   // accumulator of the sweep after next
+    long long *z = dd.Gfix + (size_t)dd.gzero * d * d;
+    for (int e = tid; e < d * d; e += T) z[e] = 0;
+  }
 
   // thread -> (block of G, row group)
   const int blk = tid % B, rg = tid / B;
@@ -229,78 +265,67 @@ __global__ void __launch_bounds__(SweepCfg<NB>::T) sweep_gram_kernel(DeviceData 
       }
   }
   // ---- order-independent accumulation across CTAs: 64-bit fixed point ----
+  // (no finalisation pass: consumers read the fixed-point buffer, internal.cuh: g_load)
   if (rg == 0) {
+    long long *Gacc = dd.Gfix + (size_t)dd.gcur * d * d;
+    double inv[4][4];                                  // scales first: the atomics below must not wait on these loads
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int gi = 4 * bi + p, gj = 4 * bj + q;
+        inv[p][q] = (gi < d && gj < d && gi <= gj) ? dd.Ginv_scale[gi * d + gj] : 0.0;
+      }
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int gi = 4 * bi + p, gj = 4 * bj + q;
         if (gi < d && gj < d && gi <= gj) {
-          const long long f = __double2ll_rn(acc[p][q] * dd.Ginv_scale[gi * d + gj]);
-          atomicAdd(reinterpret_cast<unsigned long long *>(dd.Gfix + gi * d + gj), (unsigned long long)f);
+          const long long f = __double2ll_rn(acc[p][q] * inv[p][q]);
+          atomicAdd(reinterpret_cast<unsigned long long *>(Gacc + gi * d + gj), (unsigned long long)f);
         }
       }
-  }
-  // ---- last CTA converts to double, mirrors, and re-zeroes the accumulators ----
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(dd.ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    for (int e = tid; e < d * d; e += T) {
-      const int i = e / d, j = e - i * d;
-      if (i <= j) {
-        const long long f = __ldcg(dd.Gfix + e);
-        const double v = (double)f * dd.Gscale[e];
-        dd.G[i * d + j] = v;
-        dd.G[j * d + i] = v;
-        dd.Gfix[e] = 0;
-      }
-    }
-    if (tid == 0) *dd.ticket = 0u;
   }
 }
 
 
 // ---------------------------------------------------------------------------
-// K1 + K2 fused sweep, main path for d <= 24 (LM / SAR up to K = 22): TMA-staged.
+// K1 + K2 fused sweep, main path for d <= 24 (LM / SAR up to K = 22): TMA-fed ring.
+//
+// HBM layout (packed once at create, see api.cu): the rows are cut into tiles of R = 64;
+//   Zt   [ntiles][m+1][R]  column-major inside a tile, columns = X_1..X_m, y; zero padded
+//   blob per tile, 16-byte aligned: int rp_local[R+4] | double va[nz~2] | int ci[nz~4]
+// so one tile is TWO contiguous bulk copies (cp.async.bulk, complete_tx on an mbarrier).
 //
 // One persistent, warp-specialised CTA per SM around an S-stage shared-memory ring:
-//   producer warp : per tile of R rows, 1-D TMA bulk copies (cp.async.bulk, complete_tx on
-//                   an mbarrier) of the K column segments of X (X is kept COLUMN-major and
-//                   zero-padded to a whole number of tiles, so a tile column is one
-//                   contiguous R*8-byte run), of y, and of the tile's CSR slice
-//                   (row_ptr, col_idx, val).  Nothing N-scale passes through registers.
-//   gather warps  : spatial lag of the tile, Wy[r] = sum_p val[p] * y[col[p]] (CSR slice
-//                   from shared memory, y gathered from L2), written as column 1 of the tile.
-//   math warps    : lane = row, warp = one 6x6 block of G = Z'Z (diagonal blocks 21 DFMA,
-//                   off-diagonal 36 DFMA per row for 6 / 12 LDS.64); the column-major tile
-//                   makes every LDS conflict-free.  Blocks are dealt to warps so that the
-//                   four SM sub-partitions carry equal DFMA work.
+//   producer warp   : one elected lane issues the two bulk copies of a tile into a free stage.
+//   4 gather warps  : one tile each (4 tiles in flight): lane = 2 rows, Wy[r] = sum_p va[p] *
+//                     y[col[p]] in CSR order with all gathers of the lane in flight at once (CSR
+//                     slice from shared memory, y from L2), written as tile column m+1.
+//   math warps      : lane = row, warp = one 6x6 block of G = Z'Z (diagonal blocks 21 DFMA,
+//                     off-diagonal 36 DFMA per row for 6 / 12 conflict-free LDS.64).
 // full[s] / lag[s] / empty[s] mbarriers order producer -> gather -> math -> producer.
+// Tail: per-lane partial blocks go through shared memory, one thread per entry of G adds the
+// 32 (64) lane partials in a fixed order and issues ONE 64-bit fixed-point atomic; there is
+// no finalisation pass -- consumers read the fixed-point buffer (internal.cuh: g_load).
 // ---------------------------------------------------------------------------
 struct BlockMap { unsigned char gi[32], gj[32]; };
 
 template <int NG>
-struct S7 {
+struct Ring {
   static constexpr int NBLK = NG * (NG + 1) / 2;
-  static constexpr int WPB = (NBLK >= 8) ? 1 : (NBLK >= 5 ? 2 : 4);   // math warps per block of G
+  static constexpr int WPB = (NBLK >= 8) ? 1 : 2;                    // math warps per block of G (row split)
   static constexpr int MATH = NBLK * WPB;
-  static constexpr int GATHER = 4;
+  static constexpr int GATHER = 4;                                    // gather warps = tiles whose lag is in flight
   static constexpr int T = (MATH + GATHER + 1) * 32;                 // + producer warp
-  static constexpr int RPT = 4;                                       // rows per lane per tile
-  static constexpr int R = 32 * RPT;                                  // rows per tile
+  static constexpr int R = SWEEP_TILE_ROWS;                          // rows per tile
   static constexpr int NC = 6 * NG;                                   // tile columns incl. zero padding
-  static constexpr int S = 4;                                         // ring stages
+  static constexpr int NRED = NBLK * 36;                              // entries reduced in the tail
+  static constexpr size_t RED_BYTES = (size_t)NRED * (WPB * 32 + 1) * 8;
 };
-
-constexpr int S7_MAXNZ = 2560;   // nonzeros of one tile that fit the ring
-
-__host__ __device__ inline size_t s7_stage_doubles(int R, int NC, int maxnz) {
-  // Zt[NC][R] | VA[maxnz+4] | CI[maxnz+8] (ints) | RP[R+8] (ints); maxnz % 4 == 0 keeps 16-byte alignment
-  return (size_t)R * NC + (maxnz + 4) + (maxnz + 8) / 2 + (R + 8) / 2;
-}
+constexpr int RING_MAX_STAGES = 12;
+constexpr size_t RING_SMEM_BUDGET = 200 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
@@ -325,105 +350,133 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 }
 
 template <int NG>
-__global__ void __launch_bounds__(S7<NG>::T, 1)
-sweep_tma_kernel(DeviceData dd, int ntiles, const int *__restrict__ tile_rp, int maxnz, BlockMap bm) {
-  using C = S7<NG>;
-  constexpr int T = C::T, R = C::R, NC = C::NC, S = C::S, RPT = C::RPT, WPB = C::WPB, MATH = C::MATH, GATHER = C::GATHER;
-  extern __shared__ __align__(16) double smem[];
-  __shared__ __align__(8) uint64_t full[S], lag[S], empty[S];
-  __shared__ int s_last;
-  const size_t stage_d = s7_stage_doubles(R, NC, maxnz);
+__global__ void __launch_bounds__(Ring<NG>::T, 1)
+sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, BlockMap bm) {
+  using C = Ring<NG>;
+  constexpr int T = C::T, R = C::R, NC = C::NC, WPB = C::WPB, MATH = C::MATH, GATHER = C::GATHER, NRED = C::NRED;
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ __align__(8) uint64_t full[RING_MAX_STAGES], lag[RING_MAX_STAGES], empty[RING_MAX_STAGES];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int m = dd.m, d = dd.d;
   const bool has_w = dd.model != 0;
+  const double *__restrict__ yg = dd.y;
 
-  auto stZ = [&](int s) { return smem + (size_t)s * stage_d; };
-  auto stVA = [&](int s) { return stZ(s) + (size_t)R * NC; };
-  auto stCI = [&](int s) { return reinterpret_cast<int *>(stVA(s) + maxnz + 4); };
-  auto stRP = [&](int s) { return stCI(s) + maxnz + 8; };
-
-  for (size_t e = tid; e < (size_t)S * stage_d; e += T) smem[e] = 0.0;   // padding columns stay zero
+  // the accumulator of the sweep after next: its last reader finished before this launch
+  if (blockIdx.x == 0 && dd.gzero >= 0) {
+    long long *z = dd.Gfix + (size_t)dd.gzero * d * d;
+    for (int e = tid; e < d * d; e += T) z[e] = 0;
+  }
+  // tail bookkeeping, loaded early so that its latency is off the critical path
+  int gidx = -1;
+  double inv = 0.0;
+  if (tid < NRED) {
+    const int blk = tid / 36, e = tid - blk * 36, p = e / 6, q = e - p * 6;
+    const int ca = 6 * bm.gi[blk] + p, cb = 6 * bm.gj[blk] + q;       // tile columns
+    const bool lower = bm.gi[blk] == bm.gj[blk] && q < p;
+    const int ncol = has_w ? m + 2 : m + 1;
+    if (!lower && ca < ncol && cb < ncol) {
+      const int ga = ca < m ? 2 + ca : ca - m, gb = cb < m ? 2 + cb : cb - m;   // G index: y = 0, Wy = 1, X_a = 2 + a
+      gidx = min(ga, gb) * d + max(ga, gb);
+      inv = dd.Ginv_scale[gidx];
+    }
+  }
+  auto stZ = [&](int s) { return reinterpret_cast<double *>(ring + (size_t)s * stage_bytes); };
+  auto stC = [&](int s) { return ring + (size_t)s * stage_bytes + (size_t)NC * R * 8; };
+  // columns the copies never write (padding, and Wy when there is no W) stay zero
+  {
+    const int c0 = has_w ? m + 2 : m + 1, npad = (NC - c0) * R;
+    for (int e = tid; e < S * npad; e += T) {
+      const int s = e / npad, o = e - s * npad;
+      stZ(s)[c0 * R + o] = 0.0;
+    }
+  }
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&lag[s], GATHER); mbar_init(&empty[s], MATH); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&lag[s], 1); mbar_init(&empty[s], MATH); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
-  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic zero-fill before async-proxy writes
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 
   const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const size_t ldx = (size_t)ntiles * R;                            // padded column stride of Xc / length of ypad
+  const uint32_t z_bytes = (uint32_t)(m + 1) * R * 8u;
+
+  double acc[6][6];
+#pragma unroll
+  for (int p = 0; p < 6; ++p)
+#pragma unroll
+    for (int q = 0; q < 6; ++q) acc[p][q] = 0.0;
 
   if (wid == MATH + GATHER) {
     // =========================== producer ===========================
-    int p0 = 0, p1 = 0;
-    if (has_w && my_tiles > 0) { p0 = tile_rp[blockIdx.x]; p1 = tile_rp[blockIdx.x + 1]; }
-    for (int j = 0; j < my_tiles; ++j) {
-      const int s = j % S, tile = blockIdx.x + j * gridDim.x, r0 = tile * R;
-      int q0 = 0, q1 = 0;                                           // prefetch next tile's CSR range
-      if (has_w && j + 1 < my_tiles) { q0 = tile_rp[tile + gridDim.x]; q1 = tile_rp[tile + gridDim.x + 1]; }
-      mbar_wait(&empty[s], ((j / S) & 1) ^ 1);
-      const int a0 = p0 & ~3, b0 = p0 & ~1;
-      const uint32_t ci_bytes = has_w ? (uint32_t)((p1 - a0 + 3) / 4) * 16u : 0u;
-      const uint32_t va_bytes = has_w ? (uint32_t)((p1 - b0 + 1) / 2) * 16u : 0u;
-      const uint32_t rp_bytes = has_w ? (uint32_t)(R + 4) * 4u : 0u;
-      if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)(m + 1) * R * 8u + ci_bytes + va_bytes + rp_bytes);
-      __syncwarp();
-      double *Z = stZ(s);
-      for (int c = lane; c < m; c += 32) tma_bulk_g2s(Z + (size_t)(2 + c) * R, dd.Xc + (size_t)c * ldx + r0, R * 8u, &full[s]);
-      if (lane == 31) tma_bulk_g2s(Z, dd.ypad + r0, R * 8u, &full[s]);
-      if (has_w) {
-        if (lane == 30) tma_bulk_g2s(stRP(s), dd.rp + r0, rp_bytes, &full[s]);
-        if (lane == 29 && ci_bytes) tma_bulk_g2s(stCI(s), dd.ci + a0, ci_bytes, &full[s]);
-        if (lane == 28 && va_bytes) tma_bulk_g2s(stVA(s), dd.va + b0, va_bytes, &full[s]);
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;                                                // fresh barriers: the "previous" phase is complete
+      long long o0 = 0, o1 = 0;
+      if (has_w && my_tiles > 0) { o0 = dd.tile_off[blockIdx.x]; o1 = dd.tile_off[blockIdx.x + 1]; }
+      for (int j = 0; j < my_tiles; ++j) {
+        const int tile = blockIdx.x + j * gridDim.x;
+        long long n0 = 0, n1 = 0;                                     // next tile's blob range, fetched early
+        if (has_w && j + 1 < my_tiles) { n0 = dd.tile_off[tile + gridDim.x]; n1 = dd.tile_off[tile + gridDim.x + 1]; }
+        mbar_wait(&empty[s], ph);
+        const uint32_t c_bytes = (uint32_t)(o1 - o0);
+        mbar_expect_tx(&full[s], z_bytes + c_bytes);
+        tma_bulk_g2s(stZ(s), dd.Zt + (size_t)tile * (m + 1) * R, z_bytes, &full[s]);
+        if (c_bytes) tma_bulk_g2s(stC(s), dd.csr_blob + o0, c_bytes, &full[s]);
+        o0 = n0; o1 = n1;
+        if (++s == S) { s = 0; ph ^= 1; }
       }
-      p0 = q0; p1 = q1;
     }
   } else if (wid >= MATH) {
     // =========================== gather: Wy of the tile ===========================
-    const int g = tid - MATH * 32;                                  // 0 .. 127
-    for (int j = 0; j < my_tiles; ++j) {
-      const int s = j % S, tile = blockIdx.x + j * gridDim.x, r0 = tile * R;
-      mbar_wait(&full[s], (j / S) & 1);
-      double *Z = stZ(s);
+    // one warp per tile, GATHER tiles in flight; lane -> rows lane, lane + 32; the first GU
+    // nonzeros of both rows are gathered with every load in flight, longer rows finish serially
+    constexpr int GU = 10;
+    const int g = wid - MATH;
+    int s = g % S;
+    uint32_t ph = (g / S) & 1;
+    for (int j = g; j < my_tiles; j += GATHER) {
+      mbar_wait(&full[s], ph);
       if (has_w) {
-        const int *RP = stRP(s), *CI = stCI(s);
-        const double *VA = stVA(s);
-        const int p0 = RP[0], a0 = p0 & ~3, b0 = p0 & ~1;
-        for (int r = g; r < R; r += GATHER * 32) {
-          double acc = 0.0;
-          if (r0 + r < dd.n) {
-            const int pb = RP[r], pe = RP[r + 1];
-            int p = pb;
-            for (; p + 4 <= pe; p += 4) {                           // four gathers in flight
-              const double y0 = dd.y[CI[p - a0]], y1 = dd.y[CI[p + 1 - a0]], y2 = dd.y[CI[p + 2 - a0]], y3 = dd.y[CI[p + 3 - a0]];
-              acc = fma(VA[p - b0], y0, acc); acc = fma(VA[p + 1 - b0], y1, acc);
-              acc = fma(VA[p + 2 - b0], y2, acc); acc = fma(VA[p + 3 - b0], y3, acc);
-            }
-            for (; p < pe; ++p) acc = fma(VA[p - b0], dd.y[CI[p - a0]], acc);
-          }
-          Z[R + r] = acc;                                           // column 1 = Wy
+        double *Z = stZ(s);
+        const int *RP = reinterpret_cast<const int *>(stC(s));
+        const int nz = RP[R];
+        const double *VA = reinterpret_cast<const double *>(stC(s) + (R + 4) * 4);
+        const int *CI = reinterpret_cast<const int *>(VA + ((nz + 1) & ~1));
+        int pb[R / 32], pe[R / 32];
+        double yv[R / 32][GU];
+#pragma unroll
+        for (int hh = 0; hh < R / 32; ++hh) {
+          pb[hh] = RP[lane + 32 * hh]; pe[hh] = RP[lane + 32 * hh + 1];
+#pragma unroll
+          for (int u = 0; u < GU; ++u) yv[hh][u] = pb[hh] + u < pe[hh] ? __ldg(yg + CI[pb[hh] + u]) : 0.0;
         }
+#pragma unroll
+        for (int hh = 0; hh < R / 32; ++hh) {
+          double a = 0.0;                                             // CSR order, fused multiply-add (as K1)
+#pragma unroll
+          for (int u = 0; u < GU; ++u) if (pb[hh] + u < pe[hh]) a = fma(VA[pb[hh] + u], yv[hh][u], a);
+          for (int p = pb[hh] + GU; p < pe[hh]; ++p) a = fma(VA[p], __ldg(yg + CI[p]), a);
+          Z[(m + 1) * R + lane + 32 * hh] = a;
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); // generic writes before the stage is refilled
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&lag[s]);
+      s += GATHER;
+      while (s >= S) { s -= S; ph ^= 1; }
     }
   } else {
     // =========================== math: this warp's 6x6 block ===========================
     const int blk = wid % C::NBLK, wr = wid / C::NBLK;
     const int gi = bm.gi[blk], gj = bm.gj[blk];
     const bool diag = gi == gj;
-    double acc[6][6];
-#pragma unroll
-    for (int p = 0; p < 6; ++p)
-#pragma unroll
-      for (int q = 0; q < 6; ++q) acc[p][q] = 0.0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int j = 0; j < my_tiles; ++j) {
-      const int s = j % S;
-      mbar_wait(&full[s], (j / S) & 1);
-      mbar_wait(&lag[s], (j / S) & 1);
+      mbar_wait(&lag[s], ph);
       const double *Z = stZ(s);
 #pragma unroll
-      for (int rr = 0; rr < RPT / WPB; ++rr) {
+      for (int rr = 0; rr < (R / 32) / WPB; ++rr) {
         const int r = lane + 32 * (wr + WPB * rr);
         double a[6], b[6];
 #pragma unroll
@@ -444,39 +497,28 @@ sweep_tma_kernel(DeviceData dd, int ntiles, const int *__restrict__ tile_rp, int
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
+      if (++s == S) { s = 0; ph ^= 1; }
     }
-    // lanes hold disjoint rows: fixed-order shuffle tree, then order-independent fixed-point atomics
+  }
+  // ---- tail: lane partials -> shared memory -> one thread per entry -> one atomic ----
+  __syncthreads();                                                    // every stage has been consumed
+  double *red = reinterpret_cast<double *>(ring);
+  constexpr int LD = WPB * 32 + 1;
+  if (wid < MATH) {
+    const int blk = wid % C::NBLK, wr = wid / C::NBLK;
 #pragma unroll
     for (int p = 0; p < 6; ++p)
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        if (diag && q < p) continue;
-        const double v = warp_sum(acc[p][q]);
-        const int ci_ = 6 * gi + p, cj_ = 6 * gj + q;
-        if (lane == 0 && ci_ < d && cj_ < d) {
-          const long long f = __double2ll_rn(v * dd.Ginv_scale[ci_ * d + cj_]);
-          atomicAdd(reinterpret_cast<unsigned long long *>(dd.Gfix + ci_ * d + cj_), (unsigned long long)f);
-        }
-      }
+      for (int q = 0; q < 6; ++q) red[(blk * 36 + p * 6 + q) * LD + wr * 32 + lane] = acc[p][q];
   }
-  // ---- last CTA converts to double, mirrors, and re-zeroes the accumulators ----
-  __threadfence();
   __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(dd.ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    for (int e = tid; e < d * d; e += T) {
-      const int i = e / d, j2 = e - i * d;
-      if (i <= j2) {
-        const long long f = __ldcg(dd.Gfix + e);
-        const double v = (double)f * dd.Gscale[e];
-        dd.G[i * d + j2] = v;
-        dd.G[j2 * d + i] = v;
-        dd.Gfix[e] = 0;
-      }
-    }
-    if (tid == 0) *dd.ticket = 0u;
+  if (gidx >= 0) {
+    const double *v = red + tid * LD;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;                    // fixed order
+#pragma unroll 8
+    for (int l = 0; l < WPB * 32; l += 4) { s0 += v[l]; s1 += v[l + 1]; s2 += v[l + 2]; s3 += v[l + 3]; }
+    const long long f = __double2ll_rn(((s0 + s1) + (s2 + s3)) * inv);
+    atomicAdd(reinterpret_cast<unsigned long long *>(dd.Gfix + (size_t)dd.gcur * d * d + gidx), (unsigned long long)f);
   }
 }
 
@@ -494,22 +536,27 @@ __global__ void gram_generic_kernel(DeviceData dd) {
     for (int row = lane; row < dd.n; row += 32)
       acc = fma(z_entry(dd, row, i), z_entry(dd, row, j), acc);
     acc = warp_sum(acc);
-    if (lane == 0) { dd.G[i * d + j] = acc; dd.G[j * d + i] = acc; }
+    if (lane == 0) dd.Gfix[(size_t)dd.gcur * d * d + i * d + j] = __double2ll_rn(acc * dd.Ginv_scale[i * d + j]);
   }
 }
 
 bool sweep_fast_supported(const DeviceData &dd) { return dd.d <= 88; }
 
-int sweep_tma_rows_per_tile(int d) { return d <= 24 ? S7<4>::R : 0; }
-bool sweep_tma_supported(const DeviceData &dd) {
-  return dd.d <= 24 && dd.model != 2 && dd.Xc != nullptr && (dd.model == 0 || dd.tile_rp != nullptr) &&
-         dd.tile_maxnz <= S7_MAXNZ;
+// ring geometry for a given design: stages that fit the shared-memory budget (0 = use the other paths)
+int sweep_ring_stage_bytes(int d, int max_blob) { return d <= 24 ? 6 * ((d + 5) / 6) * SWEEP_TILE_ROWS * 8 + max_blob : 0; }
+static int ring_stages(int d, int max_blob) {
+  const int sb = sweep_ring_stage_bytes(d, max_blob);
+  if (sb == 0) return 0;
+  int S = (int)(RING_SMEM_BUDGET / sb);
+  if (S > RING_MAX_STAGES) S = RING_MAX_STAGES;
+  return S >= 3 ? S : 0;
 }
+bool sweep_ring_supported(int d, int model, int max_blob) { return model != 2 && ring_stages(d, max_blob) > 0; }
 
 // deal the blocks of G to warps so that the four SM sub-partitions (warp % 4) carry equal DFMA work
 template <int NG>
 static BlockMap make_block_map() {
-  using C = S7<NG>;
+  using C = Ring<NG>;
   BlockMap bm{};
   int gi[32], gj[32], nb = 0;
   for (int i = 0; i < NG; ++i) for (int j = i + 1; j < NG; ++j) { gi[nb] = i; gj[nb] = j; ++nb; }   // 36 FMAs per row
@@ -530,18 +577,20 @@ static BlockMap make_block_map() {
 }
 
 template <int NG>
-static void launch_sweep_tma(const DeviceData &dd, int sm_count, cudaStream_t s) {
-  using C = S7<NG>;
+static void launch_sweep_ring(const DeviceData &dd, int sm_count, cudaStream_t s) {
+  using C = Ring<NG>;
   static BlockMap bm = make_block_map<NG>();
-  const size_t smem = (size_t)C::S * s7_stage_doubles(C::R, C::NC, dd.tile_maxnz) * sizeof(double);
+  const int S = ring_stages(dd.d, dd.tile_max_blob), sb = sweep_ring_stage_bytes(dd.d, dd.tile_max_blob);
+  size_t smem = (size_t)S * sb;
+  if (smem < C::RED_BYTES) smem = C::RED_BYTES;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaFuncSetAttribute(sweep_tma_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(sweep_ring_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
   const int ntiles = (dd.n + C::R - 1) / C::R;
   const int grid = ntiles < sm_count ? ntiles : sm_count;
-  sweep_tma_kernel<NG><<<grid, C::T, smem, s>>>(dd, ntiles, dd.tile_rp, dd.tile_maxnz, bm);
+  sweep_ring_kernel<NG><<<grid, C::T, smem, s>>>(dd, ntiles, S, sb, bm);
 }
 
 template <int NB>
@@ -567,11 +616,11 @@ void launch_sweep(const DeviceData &dd, int sm_count, cudaStream_t s) {
     gram_generic_kernel<<<296, 256, 0, s>>>(dd);
     return;
   }
-  if (sweep_tma_supported(dd)) {
-    if (dd.d <= 6) launch_sweep_tma<1>(dd, sm_count, s);
-    else if (dd.d <= 12) launch_sweep_tma<2>(dd, sm_count, s);
-    else if (dd.d <= 18) launch_sweep_tma<3>(dd, sm_count, s);
-    else launch_sweep_tma<4>(dd, sm_count, s);
+  if (dd.Zt != nullptr) {                       // packed at create iff the ring covers this design
+    if (dd.d <= 6) launch_sweep_ring<1>(dd, sm_count, s);
+    else if (dd.d <= 12) launch_sweep_ring<2>(dd, sm_count, s);
+    else if (dd.d <= 18) launch_sweep_ring<3>(dd, sm_count, s);
+    else launch_sweep_ring<4>(dd, sm_count, s);
     return;
   }
   const int nb = (dd.d + 3) / 4;

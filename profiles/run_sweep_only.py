@@ -11,8 +11,8 @@ model = sys.argv[1] if len(sys.argv) > 1 else "sar"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 p = make_problem(model, n=n, k_reg=20, knn=10)
-code = capi.MODEL_SAR if model == "sar" else capi.MODEL_SEM
-with capi.Handle(p.y, p.X, model=code, W=p.W, ldet=capi.LDET_CHEBYSHEV, cheb_order=8, cheb_probes=4,
+code = {"sar": capi.MODEL_SAR, "sem": capi.MODEL_SEM, "lm": capi.MODEL_LM}[model]
+with capi.Handle(p.y, p.X, model=code, W=p.W if model != "lm" else None, ldet=capi.LDET_CHEBYSHEV if model != "lm" else capi.LDET_NONE, cheb_order=8, cheb_probes=4,
                  n_chains=64, seed=1) as h:
     h.launch_sweep(3)
     h.sync()
@@ -20,5 +20,5 @@ with capi.Handle(p.y, p.X, model=code, W=p.W, ldet=capi.LDET_CHEBYSHEV, cheb_ord
     h.launch_sweep(reps)
     h.sync()
     dt = time.perf_counter() - t0
-    print(f"sweep: {1e6 * dt / reps:.2f} us per launch (host timed, back to back), "
+    print(f"{model} n={n} sweep: {1e6 * dt / reps:.2f} us per launch (host timed, back to back), "
           f"{h.sweep_bytes() / (dt / reps) / 1e9:.0f} GB/s algorithmic")
