@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(SweepCfg<NB>::T) sweep_gram_kernel(DeviceData 
 //
 // One persistent, warp-specialised CTA per SM around an S-stage shared-memory ring:
 //   producer warp   : one elected lane issues the two bulk copies of a tile into a free stage.
-//   4 gather warps  : one tile each (4 tiles in flight): lane = 2 rows, Wy[r] = sum_p va[p] *
+//   7 gather warps  : one tile each (7 tiles in flight): lane = 2 rows, Wy[r] = sum_p va[p] *
 //                     y[col[p]] in CSR order with all gathers of the lane in flight at once (CSR
 //                     slice from shared memory, y from L2), written as tile column m+1.
 //   math warps      : lane = row, warp = one 6x6 block of G = Z'Z (diagonal blocks 21 DFMA,
@@ -312,13 +312,42 @@ __global__ void __launch_bounds__(SweepCfg<NB>::T) sweep_gram_kernel(DeviceData 
 // ---------------------------------------------------------------------------
 struct BlockMap { unsigned char gi[32], gj[32]; };
 
+// deal the blocks of G to math warps so that the four SM sub-partitions (warp % 4) carry equal DFMA work
+template <int NG>
+constexpr BlockMap make_block_map() {
+  constexpr int NBLK = NG * (NG + 1) / 2;
+  BlockMap bm{};
+  int gi[32] = {}, gj[32] = {}, nb = 0;
+  for (int i = 0; i < NG; ++i) for (int j = i + 1; j < NG; ++j) { gi[nb] = i; gj[nb] = j; ++nb; }   // 36 FMAs per row
+  for (int i = 0; i < NG; ++i) { gi[nb] = i; gj[nb] = i; ++nb; }                                       // 21 FMAs per row
+  int load[4] = {0, 0, 0, 0}, used[32] = {};
+  for (int b = 0; b < nb; ++b) {
+    int best = -1;
+    for (int w = 0; w < NBLK; ++w) {
+      if (used[w]) continue;
+      if (best < 0 || load[w % 4] < load[best % 4]) best = w;
+    }
+    used[best] = 1;
+    load[best % 4] += (gi[b] == gj[b]) ? 21 : 36;
+    bm.gi[best] = (unsigned char)gi[b];
+    bm.gj[best] = (unsigned char)gj[b];
+  }
+  return bm;
+}
+template <int NG> __constant__ BlockMap c_block_map = make_block_map<NG>();
+
 template <int NG>
 struct Ring {
   static constexpr int NBLK = NG * (NG + 1) / 2;
   static constexpr int WPB = (NBLK >= 8) ? 1 : 2;                    // math warps per block of G (row split)
   static constexpr int MATH = NBLK * WPB;
-  static constexpr int GATHER = 4;                                    // gather warps = tiles whose lag is in flight
-  static constexpr int T = (MATH + GATHER + 1) * 32;                 // + producer warp
+  static constexpr int MATHW = (MATH + 3) / 4 * 4;                    // roles are aligned to warpgroups (setmaxnreg)
+  static constexpr int GATHER = 7;                                    // gather warps = tiles whose lag is in flight
+  static constexpr int T = (MATHW + GATHER + 1) * 32;                // gather warps + the producer warp = 2 warpgroups
+  // setmaxnreg moves registers inside the CTA's own allocation (T x the launch-bound count, 96 here):
+  // MATHW * 32 * REG_MATH + 8 * 32 * REG_LIGHT must not exceed it
+  static constexpr int REG_MATH = 120, REG_LIGHT = 56;
+  static_assert(MATHW * 32 * REG_MATH + 8 * 32 * REG_LIGHT <= T * 96, "register pool");
   static constexpr int R = SWEEP_TILE_ROWS;                          // rows per tile
   static constexpr int NC = 6 * NG;                                   // tile columns incl. zero padding
   static constexpr int NRED = NBLK * 36;                              // entries reduced in the tail
@@ -351,9 +380,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 
 template <int NG>
 __global__ void __launch_bounds__(Ring<NG>::T, 1)
-sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, BlockMap bm) {
+sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes) {
   using C = Ring<NG>;
-  constexpr int T = C::T, R = C::R, NC = C::NC, WPB = C::WPB, MATH = C::MATH, GATHER = C::GATHER, NRED = C::NRED;
+  const BlockMap &bm = c_block_map<NG>;
+  constexpr int T = C::T, R = C::R, NC = C::NC, WPB = C::WPB, MATH = C::MATH, MATHW = C::MATHW, GATHER = C::GATHER, NRED = C::NRED;
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ __align__(8) uint64_t full[RING_MAX_STAGES], lag[RING_MAX_STAGES], empty[RING_MAX_STAGES];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -400,13 +430,11 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, BlockMap bm
   const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const uint32_t z_bytes = (uint32_t)(m + 1) * R * 8u;
 
-  double acc[6][6];
-#pragma unroll
-  for (int p = 0; p < 6; ++p)
-#pragma unroll
-    for (int q = 0; q < 6; ++q) acc[p][q] = 0.0;
+  double *red = reinterpret_cast<double *>(ring);
+  constexpr int LD = WPB * 32 + 1;
 
-  if (wid == MATH + GATHER) {
+  if (wid >= MATHW) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(C::REG_LIGHT));
+  if (wid == MATHW + GATHER) {
     // =========================== producer ===========================
     if (lane == 0) {
       int s = 0;
@@ -426,15 +454,17 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, BlockMap bm
         if (++s == S) { s = 0; ph ^= 1; }
       }
     }
-  } else if (wid >= MATH) {
+    asm volatile("bar.sync 0;\n" ::: "memory");
+  } else if (wid >= MATHW) {
     // =========================== gather: Wy of the tile ===========================
     // one warp per tile, GATHER tiles in flight; lane -> rows lane, lane + 32; the first GU
     // nonzeros of both rows are gathered with every load in flight, longer rows finish serially
     constexpr int GU = 10;
-    const int g = wid - MATH;
-    int s = g % S;
-    uint32_t ph = (g / S) & 1;
-    for (int j = g; j < my_tiles; j += GATHER) {
+    // a waiter may be at most one phase away from its barrier: never more gather warps than stages
+    const int g = wid - MATHW, ng = S < GATHER ? S : GATHER;
+    int s = g;
+    uint32_t ph = 0;
+    for (int j = g; j < (g < ng ? my_tiles : 0); j += ng) {
       mbar_wait(&full[s], ph);
       if (has_w) {
         double *Z = stZ(s);
@@ -462,17 +492,24 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, BlockMap bm
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&lag[s]);
-      s += GATHER;
-      while (s >= S) { s -= S; ph ^= 1; }
+      s += ng;
+      if (s >= S) { s -= S; ph ^= 1; }
     }
+    asm volatile("bar.sync 0;\n" ::: "memory");
   } else {
     // =========================== math: this warp's 6x6 block ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(C::REG_MATH));
     const int blk = wid % C::NBLK, wr = wid / C::NBLK;
     const int gi = bm.gi[blk], gj = bm.gj[blk];
     const bool diag = gi == gj;
+    double acc[6][6];
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int q = 0; q < 6; ++q) acc[p][q] = 0.0;
     int s = 0;
     uint32_t ph = 0;
-    for (int j = 0; j < my_tiles; ++j) {
+    for (int j = 0; j < (wid < MATH ? my_tiles : 0); ++j) {
       mbar_wait(&lag[s], ph);
       const double *Z = stZ(s);
 #pragma unroll
@@ -499,17 +536,14 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, BlockMap bm
       if (lane == 0) mbar_arrive(&empty[s]);
       if (++s == S) { s = 0; ph ^= 1; }
     }
-  }
-  // ---- tail: lane partials -> shared memory -> one thread per entry -> one atomic ----
-  __syncthreads();                                                    // every stage has been consumed
-  double *red = reinterpret_cast<double *>(ring);
-  constexpr int LD = WPB * 32 + 1;
-  if (wid < MATH) {
-    const int blk = wid % C::NBLK, wr = wid / C::NBLK;
+    // ---- tail: lane partials -> shared memory -> one thread per entry -> one atomic ----
+    asm volatile("bar.sync 0;\n" ::: "memory");                       // every stage has been consumed
+    if (wid < MATH) {
 #pragma unroll
-    for (int p = 0; p < 6; ++p)
+      for (int p = 0; p < 6; ++p)
 #pragma unroll
-      for (int q = 0; q < 6; ++q) red[(blk * 36 + p * 6 + q) * LD + wr * 32 + lane] = acc[p][q];
+        for (int q = 0; q < 6; ++q) red[(blk * 36 + p * 6 + q) * LD + wr * 32 + lane] = acc[p][q];
+    }
   }
   __syncthreads();
   if (gidx >= 0) {
@@ -549,37 +583,15 @@ static int ring_stages(int d, int max_blob) {
   if (sb == 0) return 0;
   int S = (int)(RING_SMEM_BUDGET / sb);
   if (S > RING_MAX_STAGES) S = RING_MAX_STAGES;
+  static const int cap = getenv("BSREG_RING_STAGES") ? atoi(getenv("BSREG_RING_STAGES")) : 0;   // tuning knob
+  if (cap >= 3 && S > cap) S = cap;
   return S >= 3 ? S : 0;
 }
 bool sweep_ring_supported(int d, int model, int max_blob) { return model != 2 && ring_stages(d, max_blob) > 0; }
 
-// deal the blocks of G to warps so that the four SM sub-partitions (warp % 4) carry equal DFMA work
-template <int NG>
-static BlockMap make_block_map() {
-  using C = Ring<NG>;
-  BlockMap bm{};
-  int gi[32], gj[32], nb = 0;
-  for (int i = 0; i < NG; ++i) for (int j = i + 1; j < NG; ++j) { gi[nb] = i; gj[nb] = j; ++nb; }   // 36 FMAs per row
-  for (int i = 0; i < NG; ++i) { gi[nb] = i; gj[nb] = i; ++nb; }                                       // 21 FMAs per row
-  int load[4] = {0, 0, 0, 0}, used[32] = {0};
-  for (int b = 0; b < nb; ++b) {
-    int best = -1;
-    for (int w = 0; w < C::NBLK; ++w) {
-      if (used[w]) continue;
-      if (best < 0 || load[w % 4] < load[best % 4]) best = w;
-    }
-    used[best] = 1;
-    load[best % 4] += (gi[b] == gj[b]) ? 21 : 36;
-    bm.gi[best] = (unsigned char)gi[b];
-    bm.gj[best] = (unsigned char)gj[b];
-  }
-  return bm;
-}
-
 template <int NG>
 static void launch_sweep_ring(const DeviceData &dd, int sm_count, cudaStream_t s) {
   using C = Ring<NG>;
-  static BlockMap bm = make_block_map<NG>();
   const int S = ring_stages(dd.d, dd.tile_max_blob), sb = sweep_ring_stage_bytes(dd.d, dd.tile_max_blob);
   size_t smem = (size_t)S * sb;
   if (smem < C::RED_BYTES) smem = C::RED_BYTES;
@@ -590,7 +602,7 @@ static void launch_sweep_ring(const DeviceData &dd, int sm_count, cudaStream_t s
   }
   const int ntiles = (dd.n + C::R - 1) / C::R;
   const int grid = ntiles < sm_count ? ntiles : sm_count;
-  sweep_ring_kernel<NG><<<grid, C::T, smem, s>>>(dd, ntiles, S, sb, bm);
+  sweep_ring_kernel<NG><<<grid, C::T, smem, s>>>(dd, ntiles, S, sb);
 }
 
 template <int NB>
