@@ -284,7 +284,7 @@ def run_ours(args):
         sweep_cold = time_launches(h.launch_sweep, 20, True)
         chain_ms = time_launches(h.launch_chain_step, 400, False)
         bytes_sweep = h.sweep_bytes()
-        roof = {"kernel": "sweep_gram_kernel<6> (fused CSR SpMV + Gram reduction)", "bound": "hbm",
+        roof = {"kernel": "sweep_ring_kernel<4> (TMA-fed fused CSR SpMV + Gram reduction)", "bound": "hbm",
                 "achieved": bytes_sweep / (sweep_warm * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": bytes_sweep / (sweep_warm * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                 "algorithmic_bytes": bytes_sweep, "peak_source": peak_src,

@@ -40,10 +40,11 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     objdir = ROOT / "lib" / "obj"
     objdir.mkdir(exist_ok=True)
     nvcc = _nvcc()
+    extra = ["-DBSREG_TRACE"] if os.environ.get("BSREG_TRACE") else []   # clock64 trace points (diagnostics)
 
     def compile_one(src: str):
         obj = objdir / (src[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

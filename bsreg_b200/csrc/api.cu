@@ -3,6 +3,8 @@
 // CUDA graphs, chain sharding over GPUs.  No CPU fallback: without a usable CUDA
 // device every entry point fails with BSREG_ENOGPU / BSREG_ECUDA.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -18,6 +20,19 @@ using namespace bsreg;
 namespace {
 
 thread_local std::string g_err;
+
+// BSREG_TIMING=1: wall-clock of the create() phases on stderr (diagnostics only)
+struct PhaseTimer {
+  bool on = getenv("BSREG_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void mark(const char *what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bsreg timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
 
 int fail(int code, const char *fmt, ...) {
   char buf[512];
@@ -294,6 +309,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   DeviceData &dd = s.dd;
   dd.n = n; dd.m = m; dd.d = d; dd.model = h->model; dd.nnz = p->nnz;
 
+  PhaseTimer pt;
   // ---- W (CSR) ----
   int *rp = nullptr, *ci = nullptr; double *va = nullptr;
   if (p->nnz > 0 || h->model != BSREG_MODEL_LM || p->k_slx > 0) {
@@ -308,6 +324,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   }
   dd.rp = rp; dd.ci = ci; dd.va = va;
 
+  pt.mark("W upload");
   // ---- y, X (column-major on the host -> row-major [n][m] in HBM) ----
   double *y, *X, *tmp;
   TRY(s.alloc(&y, (size_t)n)); TRY(s.alloc(&X, (size_t)n * m));
@@ -337,6 +354,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   cudaFree(tmp);
   dd.y = y; dd.X = X;
   h->launches += 1;
+  pt.mark("y, X upload + transpose");
   // ---- tile-blocked operands of the ring sweep (sweep.cu): Zt and the per-tile CSR blobs ----
   dd.Zt = nullptr; dd.csr_blob = nullptr; dd.tile_off = nullptr; dd.tile_max_blob = 0;
   {
@@ -382,6 +400,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
     }
   }
 
+  pt.mark("tile packing");
   // ---- cached lags (R/15_sar.R:57, R/15_sem.R:63-64) ----
   dd.Wy = nullptr; dd.WX = nullptr;
   if (h->model != BSREG_MODEL_LM) {
@@ -420,6 +439,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   dd.Gscale = gscale; dd.Ginv_scale = ginv;
   enqueue_sweep(h, s, s.stream);
 
+  pt.mark("lags, scales, first sweep");
   // ---- chain state ----
   ChainState &cs = s.cs;
   cs.n_chains = n_chains; cs.chain_offset = o->chain_offset + chain_lo; cs.seed = o->seed;
@@ -482,12 +502,14 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
       if (p->col_idx[q] < 0 || p->col_idx[q] >= p->n) return fail(BSREG_EINVAL, "CSR column index out of range");
   }
   if (p->k_slx > 0 && !p->X_slx) return fail(BSREG_EINVAL, "k_slx > 0 needs X_slx");
+  PhaseTimer pt0;
   int ndev_avail = 0;
   if (cudaGetDeviceCount(&ndev_avail) != cudaSuccess || ndev_avail == 0) {
     cudaGetLastError();
     return fail(BSREG_ENOGPU, "no CUDA device available (this library has no CPU fallback)");
   }
 
+  PhaseTimer pt;
   bsreg_handle *h = new bsreg_handle();
   h->n = p->n; h->k = p->k; h->m = p->k + p->k_slx; h->model = o->model; h->prior = o->prior;
   h->ldet = o->ldet; h->stats_mode = o->stats_mode; h->n_chains = o->n_chains; h->opt = *o; h->nnz = p->nnz;
@@ -528,6 +550,7 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
     rc = setup_shard(h, s, p, o, cnt, lo);
     lo += cnt;
   }
+  pt.mark("shards total");
   // ---- log-determinant nodes ----
   if (rc == BSREG_OK && h->spatial) {
     if (o->ldet == BSREG_LDET_NODES) {
@@ -542,7 +565,9 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
     }
     if (rc == BSREG_OK) rc = set_nodes(h);
   }
+  pt.mark("log-det nodes");
   if (rc == BSREG_OK) rc = init_chains(h, false);
+  pt.mark("chain init");
   cudaSetDevice(cur);
   if (rc != BSREG_OK) { std::string keep = g_err; bsreg_destroy(h); g_err = keep; return rc; }
   *out = h;

@@ -13,6 +13,8 @@
 // algebra runs in shared memory.  The Cholesky is "bordered": right-hand sides and an
 // identity block are appended as extra rows, so forward solves and L^-1 come out of
 // the same column sweep and no serial triangular solve is left on the critical path.
+#include <cstdlib>
+
 #include "internal.cuh"
 #include "rng.cuh"
 
@@ -87,8 +89,7 @@ struct GView {
 // ---- bordered Cholesky: rows [0,m) = A (lower), rows [m,nrows) = extra rows B'.
 // On exit rows [0,m) hold L (A = L L'), extra row r holds (L^-1 b_r)'. nrows <= 3*NT.
 template <int NT>
-__device__ void chol_bordered(double *T, double *dg, int m, int nrows, int ld) {
-  const int tid = threadIdx.x;
+__device__ void chol_bordered(double *T, double *dg, int m, int nrows, int ld, int tid = threadIdx.x) {
   for (int k = 0; k < m; ++k) {
     double s[3];
 #pragma unroll
@@ -523,6 +524,274 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fast chain step: Independent prior, M <= FAST_MAX_M, LM / SAR / SEM.  Same arithmetic as
+// chain_kernel, re-scheduled so that only the sigma^2 -> beta -> lambda dependency chain is
+// serial.  One CTA of 4 warps per chain:
+//   warps 0-1  critical path: rss(beta) -> sigma^2 -> P1 -> bordered Cholesky (row = thread,
+//              pivot recomputed by every thread, one barrier per column) -> solves
+//   warp 2     random numbers that do not depend on this iteration's draws: the unit-rate gamma
+//              behind sigma^2, the M normals of the beta draw, the acceptance uniform
+//   warp 3     lambda proposal, log|I - v W| and log prior at the proposal (SEM: also the OLS
+//              rss at the proposal, its own (M+1)-row Cholesky)
+// ---------------------------------------------------------------------------
+#ifdef BSREG_TRACE
+__device__ long long g_trace[32];
+#define TRACE(i) do { if (blockIdx.x == 0 && tid == 0) g_trace[i] = clock64(); } while (0)
+#else
+#define TRACE(i) do { } while (0)
+#endif
+constexpr int FAST_MAX_M = 30;          // 2M + 3 bordered rows fit two warps
+constexpr int FAST_NT = 128;
+
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+
+// rows [0, nrows) on threads [0, 64) of the CTA; barrier `id` is shared by exactly those 64 threads
+__device__ void chol_bordered_rows64(double *T, int m, int nrows, int ld, int r, int id) {
+  const double *tr = T + r * ld;
+  for (int k = 0; k < m; ++k) {
+    const double *tk = T + k * ld;
+    double s0 = 0.0, s1 = 0.0, p0 = 0.0, p1 = 0.0;      // own row and pivot row, same order as chol_bordered
+    const bool live = r >= k && r < nrows;
+    if (live) s0 = tr[k];
+    p0 = tk[k];
+    int j = 0;
+    for (; j + 1 < k; j += 2) {
+      const double a = tk[j], b = tk[j + 1];
+      if (live) { s0 = fma(-tr[j], a, s0); s1 = fma(-tr[j + 1], b, s1); }
+      p0 = fma(-a, a, p0); p1 = fma(-b, b, p1);
+    }
+    if (j < k) { const double a = tk[j]; if (live) s0 = fma(-tr[j], a, s0); p0 = fma(-a, a, p0); }
+    const double piv = sqrt(p0 + p1);
+    const double dinv = 1.0 / piv;
+    // the diagonal is left untouched (every thread recomputes the pivot from it), so column k has
+    // no reader before the barrier and one barrier per column is enough
+    if (r > k && r < nrows) T[r * ld + k] = (s0 + s1) * dinv;
+    named_sync(id, 64);
+  }
+}
+
+struct FastSmem {
+  double *G, *T, *T2, *p0, *mu0, *beta, *mu1, *bd, *b0, *b1, *eps, *t0, *t1, *x;   // x: scalar exchange slots
+};
+enum { X_UNIT = 0, X_SIGMA2, X_UACC, X_PROP, X_LDETP, X_LPP, X_LPC, X_RSSP, X_S0, X_S1, X_S2, X_COUNT = 16 };
+
+__host__ __device__ inline size_t fast_doubles(int m, int model) {
+  const size_t d = gram_dim(m, model), ld = work_ld(m);
+  return d * d + (size_t)(2 * m + 3) * ld + (size_t)(m + 1) * ld + 11 * (size_t)m + X_COUNT;
+}
+
+__global__ void __launch_bounds__(FAST_NT) chain_fast_kernel(DeviceData dd, Priors pr, ChainState cs, const RunCtl *ctlp,
+                                                            double *draws) {
+  extern __shared__ double sm[];
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, m = dd.m, n = dd.n, d = dd.d;
+  const int ld = work_ld(m), A = aux_len(m);
+  const bool sar = dd.model == 1, sem = dd.model == 2;
+  FastSmem w;
+  w.G = sm; w.T = w.G + d * d; w.T2 = w.T + (2 * m + 3) * ld; w.p0 = w.T2 + (m + 1) * ld;
+  w.mu0 = w.p0 + m; w.beta = w.mu0 + m; w.mu1 = w.beta + m; w.bd = w.mu1 + m; w.b0 = w.bd + m; w.b1 = w.b0 + m;
+  w.eps = w.b1 + m; w.t0 = w.eps + m; w.t1 = w.t0 + m; w.x = w.t1 + m;
+  double *aux = cs.aux + (size_t)c * A;
+  const Philox ph(cs.seed, (uint32_t)(cs.chain_offset + c));
+
+  TRACE(0);
+  // ---- phase 0: everything that comes from HBM / L2, one round trip ----
+  for (int e = tid; e < d * d; e += FAST_NT) w.G[e] = g_load(dd, e / d, e - (e / d) * d);
+  for (int a = tid; a < m; a += FAST_NT) {
+    w.p0[a] = cs.p0[(size_t)c * m + a];
+    w.beta[a] = cs.beta[(size_t)c * m + a];
+    w.mu0[a] = cs.mu0[a];
+  }
+  const double lam = cs.lam[c], scale_l0 = cs.mh_scale[2 * c];
+  const long long iters0 = cs.iters[c];
+  const int step0 = cs.step[c];
+  double ldet_cur = aux[2 * m + 2], rss_cur = aux[2 * m + 3];
+  const uint32_t it = (uint32_t)(iters0 + 1);
+  const GView g{w.G, nullptr, nullptr, d, m, dd.model};
+  const int nrhs = sar ? 3 : 1;
+  __syncthreads();
+  TRACE(1);
+
+  if (wid == 2) {
+    // ---- random numbers that do not depend on this iteration's state ----
+    const double unit = ph.gamma(it, SLOT_SIGMA, pr.shape1, 1.0);
+    if (lane == 0) w.x[X_UNIT] = unit;
+    __threadfence_block();
+    named_arrive(1, 64);
+    if (lane < m) w.eps[lane] = ph.normal(it, SLOT_BETA, (uint32_t)lane);
+    if (lane == 31 && (sar || sem)) w.x[X_UACC] = ph.uniform(it, sar ? SLOT_LAMBDA_ACC : SLOT_RHO_ACC);
+  } else if (wid == 3) {
+    // ---- proposal side of the Metropolis-Hastings step ----
+    if (sar || sem) {
+      const double prop = ph.truncated_rw(it, sar ? SLOT_LAMBDA_PROP : SLOT_RHO_PROP, lam, scale_l0, pr.lam_lo, pr.lam_hi);
+      double acc = 0.0;
+      for (int k = lane; k < dd.n_nodes; k += 32) {
+        const double a = 1.0 - prop * dd.node_re[k], b = prop * dd.node_im[k];
+        acc = fma(dd.node_w[k], 0.5 * log(a * a + b * b), acc);
+      }
+      const double ldet_prop = warp_sum_c(acc);
+      const double lp = lane == 0 ? log_prior_lambda(prop, pr) : log_prior_lambda(lam, pr);
+      if (lane == 0) { w.x[X_PROP] = prop; w.x[X_LDETP] = ldet_prop; w.x[X_LPP] = lp; }
+      if (lane == 1) w.x[X_LPC] = lp;
+      if (sem) {   // OLS rss of (y - v Wy) on (X - v WX) at the proposal, R/15_sem.R:116-120
+        for (int e = lane; e < m * m; e += 32) {
+          const int a = e / m, b = e - a * m;
+          if (b <= a) w.T2[a * ld + b] = g.xx_eff(a, b, prop);
+        }
+        for (int a = lane; a < m; a += 32) w.T2[m * ld + a] = g.xy_eff(a, prop);
+        __syncwarp();
+        chol_bordered<32>(w.T2, w.t0, m, m + 1, ld, lane);   // t0 is free until phase 3 (SAR only)
+        double part = 0.0;
+        for (int a = lane; a < m; a += 32) { const double q = w.T2[m * ld + a]; part = fma(q, q, part); }
+        const double r = g.yy_eff(prop) - warp_sum_c(part);
+        if (lane == 0) w.x[X_RSSP] = r;
+      }
+    }
+  } else {
+    // ---- critical path: sigma^2, then the bordered factorisation of P1 ----
+    if (wid == 0) {
+      double part = 0.0;
+      for (int a = lane; a < m; a += 32) {
+        double t = 0.0;
+        for (int cc = 0; cc < m; ++cc) t = fma(g.xx_eff(a, cc, lam), w.beta[cc], t);
+        part = fma(w.beta[a], t - 2.0 * g.xy_eff(a, lam), part);
+      }
+      const double rss = g.yy_eff(lam) + warp_sum_c(part);
+      TRACE(2);
+      named_sync(1, 64);
+      TRACE(3);                                    // unit gamma from warp 2
+      const double sigma2 = 1.0 / (w.x[X_UNIT] / (pr.rate0 + 0.5 * rss));
+      if (lane == 0) w.x[X_SIGMA2] = sigma2;
+    }
+    named_sync(2, 64);
+    TRACE(4);
+    const double s = w.x[X_SIGMA2];
+    for (int e = tid; e < m * m; e += 64) {
+      const int a = e / m, b = e - a * m;
+      if (b <= a) w.T[a * ld + b] = g.xx_eff(a, b, lam) / s + (a == b ? w.p0[a] : 0.0);
+      w.T[(m + nrhs + a) * ld + b] = (a == b) ? 1.0 : 0.0;
+    }
+    for (int e = tid; e < nrhs * m; e += 64) {
+      const int t = e / m, a = e - t * m;
+      double v;
+      if (t == 0) v = g.xy_eff(a, lam) / s + w.p0[a] * w.mu0[a];
+      else if (t == 1) v = w.p0[a] * w.mu0[a] + g.Xy(a) / s;
+      else v = w.p0[a] * w.mu0[a] + g.XWy(a) / s;
+      w.T[(m + t) * ld + a] = v;
+    }
+    named_sync(2, 64);
+    TRACE(5);
+    chol_bordered_rows64(w.T, m, 2 * m + nrhs, ld, tid, 2);
+    TRACE(6);
+  }
+  __syncthreads();
+  TRACE(7);
+
+  // ---- phase 2: mu1, the beta draw, b0, b1 (one vector per warp, one entry per lane) ----
+  if (lane < m && (wid < 2 || sar)) {
+    const double *Y = w.T + (m + nrhs + lane) * ld;
+    const double *rhs = wid == 0 ? w.T + m * ld : wid == 1 ? w.eps : w.T + (m + wid - 1) * ld;
+    const double v = upper_dot(Y, rhs, lane, m);
+    (wid == 0 ? w.mu1 : wid == 1 ? w.bd : wid == 2 ? w.b0 : w.b1)[lane] = v;
+  }
+  __syncthreads();
+  if (tid < m) w.beta[tid] = w.mu1[tid] + w.bd[tid];
+  const double sigma2 = w.x[X_SIGMA2];
+  TRACE(8);
+
+  // ---- phase 3: the Metropolis-Hastings decision ----
+  double lam_new = lam, scale_l = scale_l0;
+  long long cnt[4];
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cnt[q] = cs.mh_cnt[(size_t)c * 8 + q];
+  }
+  if (sar) {
+    if (wid < 2 && lane < m) {      // t0 = X'X b0, t1 = X'X b1
+      const double *b = wid == 0 ? w.b0 : w.b1;
+      double s0 = 0.0;
+      for (int cc = 0; cc < m; ++cc) s0 = fma(g.XX(lane, cc), b[cc], s0);
+      (wid == 0 ? w.t0 : w.t1)[lane] = s0;
+    }
+    __syncthreads();
+    if (wid < 3) {                  // e0'e0, e1'e0, e1'e1 of R/15_sar.R:110-114, one per warp
+      double part = 0.0;
+      for (int a = lane; a < m; a += 32) {
+        if (wid == 0) part = fma(w.b0[a], w.t0[a] - 2.0 * g.Xy(a), part);
+        else if (wid == 1) part += w.b1[a] * w.t0[a] - w.b0[a] * g.XWy(a) - w.b1[a] * g.Xy(a);
+        else part = fma(w.b1[a], w.t1[a] - 2.0 * g.XWy(a), part);
+      }
+      const double tot = (wid == 0 ? g.yy() : wid == 1 ? g.yWy() : g.WyWy()) + warp_sum_c(part);
+      if (lane == 0) w.x[X_S0 + wid] = tot;
+    }
+    __syncthreads();
+  }
+  TRACE(9);
+  if ((sar || sem) && wid == 0) {
+    const double prop = w.x[X_PROP], ldet_prop = w.x[X_LDETP];
+    double rss_p, rss_c;
+    if (sar) {
+      const double e0e0 = w.x[X_S0], e1e0 = w.x[X_S1], e1e1 = w.x[X_S2];
+      rss_p = e0e0 - 2.0 * prop * e1e0 + prop * prop * e1e1;
+      rss_c = e0e0 - 2.0 * lam * e1e0 + lam * lam * e1e1;
+    } else {
+      rss_p = w.x[X_RSSP];
+      rss_c = rss_cur;
+    }
+    // lane 0: proposal, lane 1: current value (log rss evaluated side by side)
+    const double rr = lane == 0 ? rss_p : rss_c;
+    const double lpl = lane == 0 ? w.x[X_LPP] : w.x[X_LPC];
+    const double ld_ = lane == 0 ? ldet_prop : ldet_cur;
+    double post = !(rr > 0.0) ? nan("") : ld_ - 0.5 * (double)(n - m) * log(rr) + lpl;
+    const double post_c = __shfl_sync(0xffffffffu, post, 1);
+    if (lane == 0) {
+      const double pacc = exp(post - post_c);
+      const bool acc = w.x[X_UACC] < pacc;                // NaN compares false: R/20_mh.R:74
+      if (acc) { lam_new = prop; ldet_cur = ldet_prop; if (sem) rss_cur = rss_p; }
+      mh_count(cnt, acc);
+    }
+  }
+
+  TRACE(10);
+  // ---- finalize, tuning, draw store (thread 0 owns the scalars) ----
+  const RunCtl ctl = *ctlp;
+  const int step = step0 + 1;
+  const bool storing = step > ctl.n_burn && ctl.store;
+  const int row = step - ctl.n_burn - 1 - ctl.save_base;
+  const int P = m + 1 + ((sar || sem) ? 1 : 0);
+  double *dst = draws + (size_t)c * P * ctl.save_cap + row;
+  const bool row_ok = storing && row >= 0 && row < ctl.save_cap;
+  if (tid < m) {
+    const double b = w.beta[tid];
+    cs.beta[(size_t)c * m + tid] = b;
+    if (row_ok) dst[(size_t)tid * ctl.save_cap] = b;
+  }
+  if (tid == 0) {
+    if (step <= ctl.n_burn && step % 10 == 0 && step <= ctl.tune_limit && (sar || sem)) mh_tune(scale_l, cnt, ctl);
+    if (row_ok) {
+      dst[(size_t)m * ctl.save_cap] = sqrt(sigma2);
+      if (sar || sem) dst[(size_t)(m + 1) * ctl.save_cap] = lam_new;
+    }
+    cs.step[c] = step;
+    cs.sigma2[c] = sigma2; cs.lam[c] = lam_new;
+    cs.mh_scale[2 * c] = scale_l;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cs.mh_cnt[(size_t)c * 8 + q] = cnt[q];
+    cs.iters[c] = iters0 + 1;
+    aux[2 * m + 2] = ldet_cur; aux[2 * m + 3] = rss_cur;
+  }
+  TRACE(11);
+}
+
+#ifdef BSREG_TRACE
+extern "C" int bsreg_debug_trace(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 32); }
+#endif
+
+bool chain_fast_supported(const DeviceData &dd, const Priors &pr) {
+  return pr.prior == 0 && dd.m <= FAST_MAX_M && g_staged(dd.m, dd.model);
+}
+
 size_t chain_smem_bytes(int m, int model, int) { return work_doubles(m, model) * sizeof(double); }
 int chain_threads(int m) { return m <= 32 ? 32 : 128; }
 
@@ -552,6 +821,12 @@ void launch_chain_init(const DeviceData &dd, const Priors &pr, const ChainState 
 
 void launch_chain_step(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl *ctl, double *draws,
                        cudaStream_t s) {
+  static const bool no_fast = getenv("BSREG_CHAIN_GENERIC") != nullptr;   // A/B switch for tests and profiling
+  if (!no_fast && chain_fast_supported(dd, pr)) {
+    const size_t smem = fast_doubles(dd.m, dd.model) * sizeof(double);
+    chain_fast_kernel<<<cs.n_chains, FAST_NT, smem, s>>>(dd, pr, cs, ctl, draws);
+    return;
+  }
   InitArgs ia{};
   launch_chain(dd, pr, cs, ctl, draws, MODE_STEP, ia, s);
 }
