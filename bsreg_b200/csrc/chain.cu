@@ -547,158 +547,197 @@ constexpr int FAST_NT = 128;
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 
-// rows [0, nrows) on threads [0, 64) of the CTA; barrier `id` is shared by exactly those 64 threads
-__device__ void chol_bordered_rows64(double *T, int m, int nrows, int ld, int r, int id) {
-  const double *tr = T + r * ld;
-  for (int k = 0; k < m; ++k) {
-    const double *tk = T + k * ld;
-    double s0 = 0.0, s1 = 0.0, p0 = 0.0, p1 = 0.0;      // own row and pivot row, same order as chol_bordered
-    const bool live = r >= k && r < nrows;
-    if (live) s0 = tr[k];
-    p0 = tk[k];
-    int j = 0;
-    for (; j + 1 < k; j += 2) {
-      const double a = tk[j], b = tk[j + 1];
-      if (live) { s0 = fma(-tr[j], a, s0); s1 = fma(-tr[j + 1], b, s1); }
-      p0 = fma(-a, a, p0); p1 = fma(-b, b, p1);
-    }
-    if (j < k) { const double a = tk[j]; if (live) s0 = fma(-tr[j], a, s0); p0 = fma(-a, a, p0); }
-    const double piv = sqrt(p0 + p1);
-    const double dinv = 1.0 / piv;
-    // the diagonal is left untouched (every thread recomputes the pivot from it), so column k has
-    // no reader before the barrier and one barrier per column is enough
-    if (r > k && r < nrows) T[r * ld + k] = (s0 + s1) * dinv;
-    named_sync(id, 64);
+// sum_{k=j}^{m-1} Y[k] v[k] with four independent accumulators (FP64 latency, not throughput, binds here)
+__device__ __forceinline__ double dot_from(const double *Y, const double *v, int j, int m) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int k = j;
+  for (; k + 3 < m; k += 4) {
+    s0 = fma(Y[k], v[k], s0); s1 = fma(Y[k + 1], v[k + 1], s1); s2 = fma(Y[k + 2], v[k + 2], s2); s3 = fma(Y[k + 3], v[k + 3], s3);
   }
+  for (; k < m; ++k) s0 = fma(Y[k], v[k], s0);
+  return (s0 + s1) + (s2 + s3);
 }
 
-struct FastSmem {
-  double *G, *T, *T2, *p0, *mu0, *beta, *mu1, *bd, *b0, *b1, *eps, *t0, *t1, *x;   // x: scalar exchange slots
-};
-enum { X_UNIT = 0, X_SIGMA2, X_UACC, X_PROP, X_LDETP, X_LPP, X_LPC, X_RSSP, X_S0, X_S1, X_S2, X_COUNT = 16 };
+enum { X_UNIT = 0, X_SIGMA2, X_SD, X_UACC, X_PROP, X_LDETP, X_LPP, X_LPC, X_RSSP, X_S0, X_S1, X_S2, X_COUNT = 16 };
 
+template <int MMAX>
 __host__ __device__ inline size_t fast_doubles(int m, int model) {
   const size_t d = gram_dim(m, model), ld = work_ld(m);
-  return d * d + (size_t)(2 * m + 3) * ld + (size_t)(m + 1) * ld + 11 * (size_t)m + X_COUNT;
+  return d * d + 2 * 64 + (size_t)64 * (MMAX | 1) + 3 * MMAX + 2 * MMAX + (size_t)(m + 1) * ld + 10 * (size_t)m + X_COUNT;
 }
 
+// The K x K system is solved in the sigma^2-scaled form Q = X*'X* + sigma^2 P0 (so nothing on the
+// critical path divides by sigma^2; only the diagonal and the right-hand sides wait for the draw):
+//   mu1 = Q^-1 (X*'y* + sigma^2 P0 mu0),  beta = mu1 + sigma Q^-1/2 eps,  b0, b1 alike (R/15_sar.R:105-109).
+// Q = L D L' is eliminated right-looking with ONE ROW PER THREAD IN REGISTERS, bordered by the
+// right-hand sides and an identity block (so z = L^-1 rhs and D^-1 L^-1 fall out of the same sweep);
+// per column: publish the column, one barrier, reciprocal of the pivot, rank-1 update.
+template <int MMAX>
 __global__ void __launch_bounds__(FAST_NT) chain_fast_kernel(DeviceData dd, Priors pr, ChainState cs, const RunCtl *ctlp,
                                                             double *draws) {
   extern __shared__ double sm[];
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, m = dd.m, n = dd.n, d = dd.d;
   const int ld = work_ld(m), A = aux_len(m);
+  constexpr int LDY = MMAX | 1;
   const bool sar = dd.model == 1, sem = dd.model == 2;
-  FastSmem w;
-  w.G = sm; w.T = w.G + d * d; w.T2 = w.T + (2 * m + 3) * ld; w.p0 = w.T2 + (m + 1) * ld;
-  w.mu0 = w.p0 + m; w.beta = w.mu0 + m; w.mu1 = w.beta + m; w.bd = w.mu1 + m; w.b0 = w.bd + m; w.b1 = w.b0 + m;
-  w.eps = w.b1 + m; w.t0 = w.eps + m; w.t1 = w.t0 + m; w.x = w.t1 + m;
+  double *G = sm, *col = G + d * d, *Yd = col + 128, *Z = Yd + 64 * LDY, *dvec = Z + 3 * MMAX, *sq = dvec + MMAX;   // Yd doubles as the staging area of the bordered rows
+  double *T2 = sq + MMAX, *p0 = T2 + (m + 1) * ld, *mu0 = p0 + m, *beta = mu0 + m, *mu1 = beta + m, *bd = mu1 + m;
+  double *b0 = bd + m, *b1 = b0 + m, *eps = b1 + m, *t0 = eps + m, *t1 = t0 + m, *x = t1 + m;
   double *aux = cs.aux + (size_t)c * A;
   const Philox ph(cs.seed, (uint32_t)(cs.chain_offset + c));
+  const GView g{G, nullptr, nullptr, d, m, dd.model};
+  const int nrhs = sar ? 3 : 1, nrows = 2 * m + nrhs;
 
   TRACE(0);
-  // ---- phase 0: everything that comes from HBM / L2, one round trip ----
-  for (int e = tid; e < d * d; e += FAST_NT) w.G[e] = g_load(dd, e / d, e - (e / d) * d);
-  for (int a = tid; a < m; a += FAST_NT) {
-    w.p0[a] = cs.p0[(size_t)c * m + a];
-    w.beta[a] = cs.beta[(size_t)c * m + a];
-    w.mu0[a] = cs.mu0[a];
-  }
-  const double lam = cs.lam[c], scale_l0 = cs.mh_scale[2 * c];
+  // ---- phase 0: one round trip to L2 for the state and the Gram matrix; warp 2 draws meanwhile ----
   const long long iters0 = cs.iters[c];
+  const uint32_t it = (uint32_t)(iters0 + 1);
+  const double lam = cs.lam[c];
+  if (wid == 2) {
+    // random numbers that do not depend on this iteration's state (R/10_lm.R:178, R/00_aux.R:65, R/20_mh.R:74)
+    const double unit = ph.gamma(it, SLOT_SIGMA, pr.shape1, 1.0);
+    if (lane == 0) x[X_UNIT] = unit;
+  } else {
+    const int t3 = wid == 3 ? 64 + lane : tid;                       // 96 staging threads
+    const long long *gf = dd.Gfix + (size_t)dd.gcur * d * d;
+    for (int i = t3 >> 5; i < d; i += 3)
+      for (int j = lane; j < d; j += 32) {
+        const int e = i <= j ? i * d + j : j * d + i;
+        G[i * d + j] = (double)gf[e] * dd.Gscale[e];
+      }
+    for (int a = t3; a < m; a += 96) {
+      p0[a] = cs.p0[(size_t)c * m + a];
+      beta[a] = cs.beta[(size_t)c * m + a];
+      mu0[a] = cs.mu0[a];
+    }
+  }
+  const double scale_l0 = cs.mh_scale[2 * c];
   const int step0 = cs.step[c];
   double ldet_cur = aux[2 * m + 2], rss_cur = aux[2 * m + 3];
-  const uint32_t it = (uint32_t)(iters0 + 1);
-  const GView g{w.G, nullptr, nullptr, d, m, dd.model};
-  const int nrhs = sar ? 3 : 1;
   __syncthreads();
   TRACE(1);
 
+  double a[MMAX];                                                    // this thread's row of the bordered system
+  if (wid != 3) {
+    // sigma^2-free part of [Q; rhs'; I], built cooperatively (no divergence), one row per later owner
+    const int t3 = tid;                                              // 96 threads
+    for (int r = t3 >> 5; r < nrows; r += 3)
+      for (int j = lane; j < m; j += 32) {
+        double v;
+        if (r < m) v = j <= r ? g.xx_eff(r, j, lam) : 0.0;
+        else if (r == m) v = g.xy_eff(j, lam);
+        else if (r < m + nrhs) v = r == m + 1 ? g.Xy(j) : g.XWy(j);
+        else v = (r - m - nrhs == j) ? 1.0 : 0.0;
+        Yd[r * LDY + j] = v;
+      }
+  }
   if (wid == 2) {
-    // ---- random numbers that do not depend on this iteration's state ----
-    const double unit = ph.gamma(it, SLOT_SIGMA, pr.shape1, 1.0);
-    if (lane == 0) w.x[X_UNIT] = unit;
     __threadfence_block();
-    named_arrive(1, 64);
-    if (lane < m) w.eps[lane] = ph.normal(it, SLOT_BETA, (uint32_t)lane);
-    if (lane == 31 && (sar || sem)) w.x[X_UACC] = ph.uniform(it, sar ? SLOT_LAMBDA_ACC : SLOT_RHO_ACC);
+    named_arrive(3, 96);
+    if (lane < m) eps[lane] = ph.normal(it, SLOT_BETA, (uint32_t)lane);
+    if (lane == 31 && (sar || sem)) x[X_UACC] = ph.uniform(it, sar ? SLOT_LAMBDA_ACC : SLOT_RHO_ACC);
   } else if (wid == 3) {
-    // ---- proposal side of the Metropolis-Hastings step ----
+    // ---- sigma^2 (R/10_lm.R:174-179), then the proposal side of the Metropolis-Hastings step ----
+    double part = 0.0;
+    if (lane < m) {
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+      int cc = 0;
+      for (; cc + 3 < m; cc += 4) {
+        u0 = fma(g.xx_eff(lane, cc, lam), beta[cc], u0); u1 = fma(g.xx_eff(lane, cc + 1, lam), beta[cc + 1], u1);
+        u2 = fma(g.xx_eff(lane, cc + 2, lam), beta[cc + 2], u2); u3 = fma(g.xx_eff(lane, cc + 3, lam), beta[cc + 3], u3);
+      }
+      for (; cc < m; ++cc) u0 = fma(g.xx_eff(lane, cc, lam), beta[cc], u0);
+      part = beta[lane] * (((u0 + u1) + (u2 + u3)) - 2.0 * g.xy_eff(lane, lam));
+    }
+    const double rss = g.yy_eff(lam) + warp_sum_c(part);
+    const double sigma2 = (pr.rate0 + 0.5 * rss) / x[X_UNIT];        // 1 / Gamma(shape1, rate1)
+    if (lane == 0) x[X_SIGMA2] = sigma2;
+    __threadfence_block();
+    named_arrive(1, 96);
+    if (lane == 0) x[X_SD] = sqrt(sigma2);
     if (sar || sem) {
       const double prop = ph.truncated_rw(it, sar ? SLOT_LAMBDA_PROP : SLOT_RHO_PROP, lam, scale_l0, pr.lam_lo, pr.lam_hi);
       double acc = 0.0;
       for (int k = lane; k < dd.n_nodes; k += 32) {
-        const double a = 1.0 - prop * dd.node_re[k], b = prop * dd.node_im[k];
-        acc = fma(dd.node_w[k], 0.5 * log(a * a + b * b), acc);
+        const double aa = 1.0 - prop * dd.node_re[k], bb = prop * dd.node_im[k];
+        acc = fma(dd.node_w[k], 0.5 * log(aa * aa + bb * bb), acc);
       }
       const double ldet_prop = warp_sum_c(acc);
       const double lp = lane == 0 ? log_prior_lambda(prop, pr) : log_prior_lambda(lam, pr);
-      if (lane == 0) { w.x[X_PROP] = prop; w.x[X_LDETP] = ldet_prop; w.x[X_LPP] = lp; }
-      if (lane == 1) w.x[X_LPC] = lp;
+      if (lane == 0) { x[X_PROP] = prop; x[X_LDETP] = ldet_prop; x[X_LPP] = lp; }
+      if (lane == 1) x[X_LPC] = lp;
       if (sem) {   // OLS rss of (y - v Wy) on (X - v WX) at the proposal, R/15_sem.R:116-120
         for (int e = lane; e < m * m; e += 32) {
-          const int a = e / m, b = e - a * m;
-          if (b <= a) w.T2[a * ld + b] = g.xx_eff(a, b, prop);
+          const int r = e / m, b = e - r * m;
+          if (b <= r) T2[r * ld + b] = g.xx_eff(r, b, prop);
         }
-        for (int a = lane; a < m; a += 32) w.T2[m * ld + a] = g.xy_eff(a, prop);
+        for (int r = lane; r < m; r += 32) T2[m * ld + r] = g.xy_eff(r, prop);
         __syncwarp();
-        chol_bordered<32>(w.T2, w.t0, m, m + 1, ld, lane);   // t0 is free until phase 3 (SAR only)
-        double part = 0.0;
-        for (int a = lane; a < m; a += 32) { const double q = w.T2[m * ld + a]; part = fma(q, q, part); }
-        const double r = g.yy_eff(prop) - warp_sum_c(part);
-        if (lane == 0) w.x[X_RSSP] = r;
+        chol_bordered<32>(T2, t0, m, m + 1, ld, lane);               // t0 is free until phase 3 (SAR only)
+        double q2 = 0.0;
+        for (int r = lane; r < m; r += 32) { const double q = T2[m * ld + r]; q2 = fma(q, q, q2); }
+        const double r = g.yy_eff(prop) - warp_sum_c(q2);
+        if (lane == 0) x[X_RSSP] = r;
       }
     }
   } else {
-    // ---- critical path: sigma^2, then the bordered factorisation of P1 ----
-    if (wid == 0) {
-      double part = 0.0;
-      for (int a = lane; a < m; a += 32) {
-        double t = 0.0;
-        for (int cc = 0; cc < m; ++cc) t = fma(g.xx_eff(a, cc, lam), w.beta[cc], t);
-        part = fma(w.beta[a], t - 2.0 * g.xy_eff(a, lam), part);
+    // ---- critical path: one bordered row per thread, in registers ----
+    const int r = tid;
+    named_sync(3, 96);                                               // staged rows complete
+    TRACE(2);
+#pragma unroll
+    for (int j = 0; j < MMAX; ++j) a[j] = (j < m && r < nrows) ? Yd[r * LDY + j] : 0.0;
+    named_sync(1, 96);                                               // sigma^2 from warp 3
+    TRACE(3);
+    const double s2 = x[X_SIGMA2];
+#pragma unroll
+    for (int j = 0; j < MMAX; ++j)
+      if (j < m) {
+        if (r == j) a[j] = fma(s2, p0[j], a[j]);
+        else if (r >= m && r < m + nrhs) a[j] = fma(s2, p0[j] * mu0[j], a[j]);
       }
-      const double rss = g.yy_eff(lam) + warp_sum_c(part);
-      TRACE(2);
-      named_sync(1, 64);
-      TRACE(3);                                    // unit gamma from warp 2
-      const double sigma2 = 1.0 / (w.x[X_UNIT] / (pr.rate0 + 0.5 * rss));
-      if (lane == 0) w.x[X_SIGMA2] = sigma2;
+#pragma unroll
+    for (int k = 0; k < MMAX; ++k) {
+      if (k < m) {
+        double *cb = col + 64 * (k & 1);
+        cb[r] = a[k];
+        if (r >= m && r < m + nrhs) Z[(r - m) * MMAX + k] = a[k];   // z = L^-1 rhs, before scaling
+        if (r == k) dvec[k] = a[k];                                 // pivot d_k
+        named_sync(2, 64);
+        const double rk = __drcp_rn(cb[k]);
+        if (r > k && r < nrows) {
+          const double l = a[k] * rk;
+          a[k] = l;
+#pragma unroll
+          for (int j = k + 1; j < MMAX; ++j)
+            if (j < m) a[j] = fma(-l, cb[j], a[j]);
+        }
+      }
     }
-    named_sync(2, 64);
     TRACE(4);
-    const double s = w.x[X_SIGMA2];
-    for (int e = tid; e < m * m; e += 64) {
-      const int a = e / m, b = e - a * m;
-      if (b <= a) w.T[a * ld + b] = g.xx_eff(a, b, lam) / s + (a == b ? w.p0[a] : 0.0);
-      w.T[(m + nrhs + a) * ld + b] = (a == b) ? 1.0 : 0.0;
+    if (r >= m + nrhs && r < nrows) {
+      double *y = Yd + (r - m - nrhs) * LDY;
+#pragma unroll
+      for (int k = 0; k < MMAX; ++k) if (k < m) y[k] = a[k];
     }
-    for (int e = tid; e < nrhs * m; e += 64) {
-      const int t = e / m, a = e - t * m;
-      double v;
-      if (t == 0) v = g.xy_eff(a, lam) / s + w.p0[a] * w.mu0[a];
-      else if (t == 1) v = w.p0[a] * w.mu0[a] + g.Xy(a) / s;
-      else v = w.p0[a] * w.mu0[a] + g.XWy(a) / s;
-      w.T[(m + t) * ld + a] = v;
-    }
-    named_sync(2, 64);
-    TRACE(5);
-    chol_bordered_rows64(w.T, m, 2 * m + nrhs, ld, tid, 2);
-    TRACE(6);
   }
   __syncthreads();
-  TRACE(7);
+  TRACE(5);
 
   // ---- phase 2: mu1, the beta draw, b0, b1 (one vector per warp, one entry per lane) ----
+  if (wid == 1) {                                                    // D^1/2 eps for the beta draw
+    if (lane < m) sq[lane] = sqrt(dvec[lane]) * eps[lane];
+    __syncwarp();
+  }
   if (lane < m && (wid < 2 || sar)) {
-    const double *Y = w.T + (m + nrhs + lane) * ld;
-    const double *rhs = wid == 0 ? w.T + m * ld : wid == 1 ? w.eps : w.T + (m + wid - 1) * ld;
-    const double v = upper_dot(Y, rhs, lane, m);
-    (wid == 0 ? w.mu1 : wid == 1 ? w.bd : wid == 2 ? w.b0 : w.b1)[lane] = v;
+    const double *v = wid == 0 ? Z : wid == 1 ? sq : Z + (wid - 1) * MMAX;
+    const double r = dot_from(Yd + lane * LDY, v, lane, m);
+    (wid == 0 ? mu1 : wid == 1 ? bd : wid == 2 ? b0 : b1)[lane] = r;
   }
   __syncthreads();
-  if (tid < m) w.beta[tid] = w.mu1[tid] + w.bd[tid];
-  const double sigma2 = w.x[X_SIGMA2];
-  TRACE(8);
+  const double sigma2 = x[X_SIGMA2];
+  if (tid < m) beta[tid] = fma(x[X_SD], bd[tid], mu1[tid]);
+  TRACE(6);
 
   // ---- phase 3: the Metropolis-Hastings decision ----
   double lam_new = lam, scale_l = scale_l0;
@@ -709,51 +748,56 @@ __global__ void __launch_bounds__(FAST_NT) chain_fast_kernel(DeviceData dd, Prio
   }
   if (sar) {
     if (wid < 2 && lane < m) {      // t0 = X'X b0, t1 = X'X b1
-      const double *b = wid == 0 ? w.b0 : w.b1;
-      double s0 = 0.0;
-      for (int cc = 0; cc < m; ++cc) s0 = fma(g.XX(lane, cc), b[cc], s0);
-      (wid == 0 ? w.t0 : w.t1)[lane] = s0;
+      const double *b = wid == 0 ? b0 : b1;
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+      int cc = 0;
+      for (; cc + 3 < m; cc += 4) {
+        u0 = fma(g.XX(lane, cc), b[cc], u0); u1 = fma(g.XX(lane, cc + 1), b[cc + 1], u1);
+        u2 = fma(g.XX(lane, cc + 2), b[cc + 2], u2); u3 = fma(g.XX(lane, cc + 3), b[cc + 3], u3);
+      }
+      for (; cc < m; ++cc) u0 = fma(g.XX(lane, cc), b[cc], u0);
+      (wid == 0 ? t0 : t1)[lane] = (u0 + u1) + (u2 + u3);
     }
     __syncthreads();
     if (wid < 3) {                  // e0'e0, e1'e0, e1'e1 of R/15_sar.R:110-114, one per warp
       double part = 0.0;
-      for (int a = lane; a < m; a += 32) {
-        if (wid == 0) part = fma(w.b0[a], w.t0[a] - 2.0 * g.Xy(a), part);
-        else if (wid == 1) part += w.b1[a] * w.t0[a] - w.b0[a] * g.XWy(a) - w.b1[a] * g.Xy(a);
-        else part = fma(w.b1[a], w.t1[a] - 2.0 * g.XWy(a), part);
+      if (lane < m) {
+        if (wid == 0) part = b0[lane] * (t0[lane] - 2.0 * g.Xy(lane));
+        else if (wid == 1) part = b1[lane] * t0[lane] - b0[lane] * g.XWy(lane) - b1[lane] * g.Xy(lane);
+        else part = b1[lane] * (t1[lane] - 2.0 * g.XWy(lane));
       }
       const double tot = (wid == 0 ? g.yy() : wid == 1 ? g.yWy() : g.WyWy()) + warp_sum_c(part);
-      if (lane == 0) w.x[X_S0 + wid] = tot;
+      if (lane == 0) x[X_S0 + wid] = tot;
     }
     __syncthreads();
   }
-  TRACE(9);
+  TRACE(7);
   if ((sar || sem) && wid == 0) {
-    const double prop = w.x[X_PROP], ldet_prop = w.x[X_LDETP];
+    const double prop = x[X_PROP], ldet_prop = x[X_LDETP];
     double rss_p, rss_c;
     if (sar) {
-      const double e0e0 = w.x[X_S0], e1e0 = w.x[X_S1], e1e1 = w.x[X_S2];
+      const double e0e0 = x[X_S0], e1e0 = x[X_S1], e1e1 = x[X_S2];
       rss_p = e0e0 - 2.0 * prop * e1e0 + prop * prop * e1e1;
       rss_c = e0e0 - 2.0 * lam * e1e0 + lam * lam * e1e1;
     } else {
-      rss_p = w.x[X_RSSP];
+      rss_p = x[X_RSSP];
       rss_c = rss_cur;
     }
-    // lane 0: proposal, lane 1: current value (log rss evaluated side by side)
+    // lane 0: proposal, lane 1: current value (the two log rss side by side)
     const double rr = lane == 0 ? rss_p : rss_c;
-    const double lpl = lane == 0 ? w.x[X_LPP] : w.x[X_LPC];
+    const double lpl = lane == 0 ? x[X_LPP] : x[X_LPC];
     const double ld_ = lane == 0 ? ldet_prop : ldet_cur;
-    double post = !(rr > 0.0) ? nan("") : ld_ - 0.5 * (double)(n - m) * log(rr) + lpl;
+    const double post = !(rr > 0.0) ? nan("") : ld_ - 0.5 * (double)(n - m) * log(rr) + lpl;
     const double post_c = __shfl_sync(0xffffffffu, post, 1);
     if (lane == 0) {
       const double pacc = exp(post - post_c);
-      const bool acc = w.x[X_UACC] < pacc;                // NaN compares false: R/20_mh.R:74
+      const bool acc = x[X_UACC] < pacc;                  // NaN compares false: R/20_mh.R:74
       if (acc) { lam_new = prop; ldet_cur = ldet_prop; if (sem) rss_cur = rss_p; }
       mh_count(cnt, acc);
     }
   }
+  TRACE(8);
 
-  TRACE(10);
   // ---- finalize, tuning, draw store (thread 0 owns the scalars) ----
   const RunCtl ctl = *ctlp;
   const int step = step0 + 1;
@@ -763,14 +807,14 @@ __global__ void __launch_bounds__(FAST_NT) chain_fast_kernel(DeviceData dd, Prio
   double *dst = draws + (size_t)c * P * ctl.save_cap + row;
   const bool row_ok = storing && row >= 0 && row < ctl.save_cap;
   if (tid < m) {
-    const double b = w.beta[tid];
+    const double b = beta[tid];
     cs.beta[(size_t)c * m + tid] = b;
     if (row_ok) dst[(size_t)tid * ctl.save_cap] = b;
   }
   if (tid == 0) {
     if (step <= ctl.n_burn && step % 10 == 0 && step <= ctl.tune_limit && (sar || sem)) mh_tune(scale_l, cnt, ctl);
     if (row_ok) {
-      dst[(size_t)m * ctl.save_cap] = sqrt(sigma2);
+      dst[(size_t)m * ctl.save_cap] = x[X_SD];
       if (sar || sem) dst[(size_t)(m + 1) * ctl.save_cap] = lam_new;
     }
     cs.step[c] = step;
@@ -781,7 +825,7 @@ __global__ void __launch_bounds__(FAST_NT) chain_fast_kernel(DeviceData dd, Prio
     cs.iters[c] = iters0 + 1;
     aux[2 * m + 2] = ldet_cur; aux[2 * m + 3] = rss_cur;
   }
-  TRACE(11);
+  TRACE(9);
 }
 
 #ifdef BSREG_TRACE
@@ -823,8 +867,8 @@ void launch_chain_step(const DeviceData &dd, const Priors &pr, const ChainState 
                        cudaStream_t s) {
   static const bool no_fast = getenv("BSREG_CHAIN_GENERIC") != nullptr;   // A/B switch for tests and profiling
   if (!no_fast && chain_fast_supported(dd, pr)) {
-    const size_t smem = fast_doubles(dd.m, dd.model) * sizeof(double);
-    chain_fast_kernel<<<cs.n_chains, FAST_NT, smem, s>>>(dd, pr, cs, ctl, draws);
+    if (dd.m <= 24) chain_fast_kernel<24><<<cs.n_chains, FAST_NT, fast_doubles<24>(dd.m, dd.model) * sizeof(double), s>>>(dd, pr, cs, ctl, draws);
+    else chain_fast_kernel<32><<<cs.n_chains, FAST_NT, fast_doubles<32>(dd.m, dd.model) * sizeof(double), s>>>(dd, pr, cs, ctl, draws);
     return;
   }
   InitArgs ia{};

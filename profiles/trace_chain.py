@@ -17,9 +17,11 @@ with capi.Handle(p.y, p.X, model=capi.MODEL_SAR, W=p.W, ldet=capi.LDET_CHEBYSHEV
     h.sync()
     out = np.zeros(32, dtype=np.int64)
     capi.load().bsreg_debug_trace(out.ctypes.data_as(C.c_void_p))
-    names = ["start", "loads+sync", "rss", "gamma wait", "sigma2 sync", "build T", "chol", "syncthreads", "dots+beta",
-             "sar sums", "mh decision", "store"]
-    t = out[:12]
-    for i in range(1, 12):
-        print(f"{names[i]:>14s} {t[i] - t[i - 1]:7d} cycles")
-    print(f"{'total':>14s} {t[11] - t[0]:7d} cycles = {(t[11] - t[0]) / 1.965e3:.2f} us at 1965 MHz")
+    # thread 0 (critical-path warp) passes points 0,1,3..9; point 2 belongs to warp 3 and is not recorded by tid 0
+    names = {1: "loads+sync", 2: "stage rows", 3: "row load + sigma2 wait", 4: "LDL elimination", 5: "Yd store + sync", 6: "dots + beta",
+             7: "sar sums", 8: "mh decision", 9: "store"}
+    prev = out[0]
+    for i in (1, 2, 3, 4, 5, 6, 7, 8, 9):
+        print(f"{names[i]:>24s} {out[i] - prev:7d} cycles")
+        prev = out[i]
+    print(f"{'total':>24s} {out[9] - out[0]:7d} cycles = {(out[9] - out[0]) / 1.965e3:.2f} us at 1965 MHz")
