@@ -81,6 +81,7 @@ SYMBOLS = {
     "bsreg_sync": (C.c_int, [C.c_void_p]),
     "bsreg_sweep_bytes": (C.c_int64, [C.c_void_p]),
     "bsreg_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "bsreg_release_cache": (None, []),
 }
 
 _lib = None

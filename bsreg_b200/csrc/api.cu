@@ -9,7 +9,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/bsreg_cuda.h"
@@ -57,6 +59,62 @@ int fail(int code, const char *fmt, ...) {
     if (r_ != BSREG_OK) return r_; \
   } while (0)
 
+
+// ---------------------------------------------------------------------------
+// Caching device allocator.  cudaMalloc / cudaFree cost milliseconds (and now and then tens of
+// milliseconds) each, and a fit allocates ~40 buffers whose sizes repeat exactly from one fit to
+// the next (an R session calls bm() again and again), so freed blocks are kept per device and
+// reused by exact size.  Blocks are only handed back after the owning stream was synchronised.
+// bsreg_release_cache() returns everything to the driver.
+// ---------------------------------------------------------------------------
+struct FreeBlock { int dev; size_t bytes; void *ptr; };
+std::mutex g_pool_mu;
+std::vector<FreeBlock> g_pool_free;
+std::unordered_map<void *, std::pair<int, size_t>> g_pool_live;
+size_t g_pool_cached = 0;
+constexpr size_t POOL_MAX_CACHED = (size_t)16 << 30;
+
+cudaError_t pool_malloc(void **p, size_t bytes) {
+  bytes = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (size_t i = 0; i < g_pool_free.size(); ++i)
+      if (g_pool_free[i].dev == dev && g_pool_free[i].bytes == bytes) {
+        *p = g_pool_free[i].ptr;
+        g_pool_cached -= bytes;
+        g_pool_free[i] = g_pool_free.back();
+        g_pool_free.pop_back();
+        g_pool_live[*p] = {dev, bytes};
+        return cudaSuccess;
+      }
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) {            // give the cache back and retry once
+    cudaGetLastError();
+    std::vector<FreeBlock> drop;
+    { std::lock_guard<std::mutex> lk(g_pool_mu); drop.swap(g_pool_free); g_pool_cached = 0; }
+    for (const FreeBlock &b : drop) { cudaSetDevice(b.dev); cudaFree(b.ptr); }
+    cudaSetDevice(dev);
+    e = cudaMalloc(p, bytes);
+  }
+  if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(g_pool_mu); g_pool_live[*p] = {dev, bytes}; }
+  return e;
+}
+
+void pool_free(void *p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  auto it = g_pool_live.find(p);
+  if (it == g_pool_live.end()) { cudaFree(p); return; }
+  const FreeBlock b{it->second.first, it->second.second, p};
+  g_pool_live.erase(it);
+  if (g_pool_cached + b.bytes > POOL_MAX_CACHED) { cudaFree(p); return; }
+  g_pool_cached += b.bytes;
+  g_pool_free.push_back(b);
+}
+
 constexpr int GRAPH_UNROLL = 24;      // Gibbs iterations per CUDA graph launch (multiple of the 3 Gram buffers)
 constexpr int BLOCK_ITERS = 1000;     // iterations between host syncs / progress callbacks
 constexpr size_t DRAW_BUF_BYTES = (size_t)1 << 30;
@@ -81,7 +139,7 @@ struct Shard {
   template <class T>
   int alloc(T **p, size_t count) {
     void *q = nullptr;
-    CU(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    CU(pool_malloc((void **)&q, std::max<size_t>(count, 1) * sizeof(T)));
     allocs.push_back(q);
     *p = static_cast<T *>(q);
     return BSREG_OK;
@@ -215,18 +273,6 @@ int enqueue_repeated(bsreg_handle *h, Shard &s, int reps, bool sweep) {
   return BSREG_OK;
 }
 
-// tr(W^2) = sum_ij W_ij W_ji, exact from CSR (host, setup only)
-double trace_w2(int n, const int32_t *rp, const int32_t *ci, const double *va) {
-  long double acc = 0.0L;
-  for (int i = 0; i < n; ++i)
-    for (int p = rp[i]; p < rp[i + 1]; ++p) {
-      const int j = ci[p];
-      for (int q = rp[j]; q < rp[j + 1]; ++q)
-        if (ci[q] == i) acc += (long double)va[p] * va[q];
-    }
-  return (double)acc;
-}
-
 int trace_moments_dev(bsreg_handle *h, Shard &s, const bsreg_problem *prob_csr, int order, int probes, uint64_t seed,
                       double *moments) {
   const int n = h->n;
@@ -239,14 +285,24 @@ int trace_moments_dev(bsreg_handle *h, Shard &s, const bsreg_problem *prob_csr, 
         if (prob_csr->col_idx[p] == i) tr += prob_csr->val[p];
     moments[1] = (double)tr;
   }
-  if (order >= 2) moments[2] = 2.0 * trace_w2(n, prob_csr->row_ptr, prob_csr->col_idx, prob_csr->val) - n;
-  if (order < 3) return BSREG_OK;
   CU(cudaSetDevice(s.dev));
+  if (order >= 2) {   // tr(W^2) = sum_ij W_ij W_ji, exact from the CSR on the device
+    double *rowsum = nullptr, *tw2 = nullptr, host_tw2 = 0.0;
+    CU(pool_malloc((void **)&rowsum, (size_t)n * 8)); CU(pool_malloc((void **)&tw2, 8));
+    launch_trace_w2_rows(n, s.dd.rp, s.dd.ci, s.dd.va, rowsum, s.stream);
+    launch_dot(rowsum, nullptr, n, s.scratch, tw2, s.stream);
+    h->launches += 3;
+    CU(cudaMemcpyAsync(&host_tw2, tw2, 8, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    pool_free(rowsum); pool_free(tw2);
+    moments[2] = 2.0 * host_tw2 - n;
+  }
+  if (order < 3) return BSREG_OK;
   const size_t len = (size_t)n * probes;
   double *U = nullptr, *buf[3] = {nullptr, nullptr, nullptr}, *res = nullptr;
-  CU(cudaMalloc(&U, len * 8));
-  for (int b = 0; b < 3; ++b) CU(cudaMalloc(&buf[b], len * 8));
-  CU(cudaMalloc(&res, (order + 1) * 8));
+  CU(pool_malloc((void **)&U, len * 8));
+  for (int b = 0; b < 3; ++b) CU(pool_malloc((void **)&buf[b], len * 8));
+  CU(pool_malloc((void **)&res, (order + 1) * 8));
   launch_probes(U, n, probes, seed, s.stream);
   // T_1 = W U ; T_j = 2 W T_{j-1} - T_{j-2}; U stays intact for the dots u'T_j u
   launch_spmm(n, s.dd.rp, s.dd.ci, s.dd.va, U, probes, probes, buf[0], probes, 0, 1.0, nullptr, 0.0, s.stream);
@@ -265,7 +321,7 @@ int trace_moments_dev(bsreg_handle *h, Shard &s, const bsreg_problem *prob_csr, 
   CU(cudaMemcpyAsync(host.data(), res, (order + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
   CU(cudaStreamSynchronize(s.stream));
   for (int j = 3; j <= order; ++j) moments[j] = host[j] / probes;
-  cudaFree(U); cudaFree(buf[0]); cudaFree(buf[1]); cudaFree(buf[2]); cudaFree(res);
+  pool_free(U); pool_free(buf[0]); pool_free(buf[1]); pool_free(buf[2]); pool_free(res);
   return BSREG_OK;
 }
 
@@ -298,9 +354,7 @@ int set_nodes(bsreg_handle *h) {
 
 int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_options *o, int n_chains, int chain_lo) {
   CU(cudaSetDevice(s.dev));
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, s.dev));
-  s.sm_count = prop.multiProcessorCount;
+  CU(cudaDeviceGetAttribute(&s.sm_count, cudaDevAttrMultiProcessorCount, s.dev));   // (cudaGetDeviceProperties costs milliseconds)
   if (o->stream && h->shards.size() == 1) { s.stream = (cudaStream_t)o->stream; s.own_stream = false; }
   else { CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)); s.own_stream = true; }
   CU(cudaStreamCreateWithFlags(&s.aux, cudaStreamNonBlocking));
@@ -328,7 +382,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   // ---- y, X (column-major on the host -> row-major [n][m] in HBM) ----
   double *y, *X, *tmp;
   TRY(s.alloc(&y, (size_t)n)); TRY(s.alloc(&X, (size_t)n * m));
-  CU(cudaMalloc(&tmp, (size_t)n * std::max(k, std::max(p->k_slx, 1)) * 8));
+  CU(pool_malloc((void **)&tmp, (size_t)n * std::max(k, std::max(p->k_slx, 1)) * 8));
   TRY(upload(s, p->y, y, (size_t)n * 8));
   TRY(upload(s, p->X, tmp, (size_t)n * k * 8));
   launch_transpose(tmp, X, n, k, m, 0, s.stream);
@@ -336,22 +390,22 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
     double *xs_rm; int *rps = rp, *cis = ci; double *vas = va;
     CU(cudaStreamSynchronize(s.stream));
     TRY(upload(s, p->X_slx, tmp, (size_t)n * p->k_slx * 8));
-    CU(cudaMalloc(&xs_rm, (size_t)n * p->k_slx * 8));
+    CU(pool_malloc((void **)&xs_rm, (size_t)n * p->k_slx * 8));
     launch_transpose(tmp, xs_rm, n, p->k_slx, p->k_slx, 0, s.stream);
     if (p->nnz_slx > 0) {
-      CU(cudaMalloc(&rps, ((size_t)n + 1) * 4)); CU(cudaMalloc(&cis, (size_t)p->nnz_slx * 4)); CU(cudaMalloc(&vas, (size_t)p->nnz_slx * 8));
+      CU(pool_malloc((void **)&rps, ((size_t)n + 1) * 4)); CU(pool_malloc((void **)&cis, (size_t)p->nnz_slx * 4)); CU(pool_malloc((void **)&vas, (size_t)p->nnz_slx * 8));
       TRY(upload(s, p->row_ptr_slx, rps, ((size_t)n + 1) * 4));
       TRY(upload(s, p->col_idx_slx, cis, (size_t)p->nnz_slx * 4));
       TRY(upload(s, p->val_slx, vas, (size_t)p->nnz_slx * 8));
     }
     launch_spmm(n, rps, cis, vas, xs_rm, p->k_slx, p->k_slx, X, m, k, 1.0, nullptr, 0.0, s.stream);
     CU(cudaStreamSynchronize(s.stream));
-    cudaFree(xs_rm);
-    if (p->nnz_slx > 0) { cudaFree(rps); cudaFree(cis); cudaFree(vas); }
+    pool_free(xs_rm);
+    if (p->nnz_slx > 0) { pool_free(rps); pool_free(cis); pool_free(vas); }
     h->launches += 2;
   }
   CU(cudaStreamSynchronize(s.stream));
-  cudaFree(tmp);
+  pool_free(tmp);
   dd.y = y; dd.X = X;
   h->launches += 1;
   pt.mark("y, X upload + transpose");
@@ -361,7 +415,6 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
     constexpr int R = SWEEP_TILE_ROWS;
     const int ntiles = (n + R - 1) / R;
     std::vector<long long> off(ntiles + 1, 0);
-    std::vector<unsigned char> blob;
     int max_blob = 0;
     const bool with_w = h->model != BSREG_MODEL_LM;
     if (with_w) {
@@ -379,22 +432,12 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
       h->launches += 1;
       dd.Zt = zt;
       if (with_w) {
-        blob.assign((size_t)off[ntiles], 0);
-        for (int t = 0; t < ntiles; ++t) {
-          const int r0 = t * R, p0 = p->row_ptr[r0];
-          int *rpl = reinterpret_cast<int *>(blob.data() + off[t]);
-          for (int i = 0; i <= R; ++i) rpl[i] = p->row_ptr[std::min(r0 + i, n)] - p0;
-          const int nz = rpl[R];
-          double *bva = reinterpret_cast<double *>(blob.data() + off[t] + (R + 4) * 4);
-          int *bci = reinterpret_cast<int *>(bva + ((nz + 1) & ~1));
-          std::copy(p->val + p0, p->val + p0 + nz, bva);
-          std::copy(p->col_idx + p0, p->col_idx + p0 + nz, bci);
-        }
         unsigned char *db; long long *doff;
-        TRY(s.alloc(&db, blob.size() + 16)); TRY(s.alloc(&doff, (size_t)ntiles + 1));
-        TRY(upload(s, blob.data(), db, blob.size()));
+        TRY(s.alloc(&db, (size_t)off[ntiles] + 16)); TRY(s.alloc(&doff, (size_t)ntiles + 1));
         TRY(upload(s, off.data(), doff, ((size_t)ntiles + 1) * 8));
-        CU(cudaStreamSynchronize(s.stream));
+        launch_pack_csr_tiles(rp, ci, va, doff, db, n, s.stream);
+        h->launches += 1;
+        CU(cudaStreamSynchronize(s.stream));                 // `off` is a host temporary
         dd.csr_blob = db; dd.tile_off = doff; dd.tile_max_blob = max_blob;
       }
     }
@@ -462,6 +505,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   if (o->ng_beta0) { TRY(s.alloc(&s.beta0, (size_t)m)); TRY(upload(s, o->ng_beta0, s.beta0, (size_t)m * 8)); }
   CU(cudaStreamSynchronize(s.stream));
   cs.mu0 = mu0;
+  pt.mark("chain state");
   return BSREG_OK;
 }
 
@@ -587,8 +631,8 @@ void bsreg_destroy(bsreg_handle *h) {
     if (s.chain_graph) cudaGraphExecDestroy(s.chain_graph);
     for (cudaEvent_t e : s.events) cudaEventDestroy(e);
     if (s.aux) cudaStreamDestroy(s.aux);
-    for (void *q : s.allocs) cudaFree(q);
-    if (s.draws_dev) cudaFree(s.draws_dev);
+    for (void *q : s.allocs) pool_free(q);
+    if (s.draws_dev) pool_free(s.draws_dev);
     if (s.own_stream && s.stream) cudaStreamDestroy(s.stream);
   }
   cudaSetDevice(cur);
@@ -623,9 +667,9 @@ int bsreg_run(bsreg_handle *h, int32_t n_burn, int32_t n_save, const bsreg_mh *m
       CU(cudaStreamSynchronize(s.stream));
       if (s.graph) { cudaGraphExecDestroy(s.graph); s.graph = nullptr; }   // the graphs bake the buffer pointer
       if (s.chain_graph) { cudaGraphExecDestroy(s.chain_graph); s.chain_graph = nullptr; }
-      if (s.draws_dev) cudaFree(s.draws_dev);
+      if (s.draws_dev) pool_free(s.draws_dev);
       s.draws_dev = nullptr;
-      CU(cudaMalloc(&s.draws_dev, (size_t)cap * row_bytes));
+      CU(pool_malloc((void **)&s.draws_dev, (size_t)cap * row_bytes));
       s.save_cap = cap;
     }
     CU(cudaMemsetAsync(s.cs.step, 0, (size_t)s.cs.n_chains * 4, s.stream));
@@ -764,7 +808,7 @@ int bsreg_eval_spmm(bsreg_handle *h, const double *B, int32_t mcols, double *out
   CU(cudaSetDevice(s.dev));
   const size_t len = (size_t)h->n * mcols;
   double *cm, *rm, *orm;
-  CU(cudaMalloc(&cm, len * 8)); CU(cudaMalloc(&rm, len * 8)); CU(cudaMalloc(&orm, len * 8));
+  CU(pool_malloc((void **)&cm, len * 8)); CU(pool_malloc((void **)&rm, len * 8)); CU(pool_malloc((void **)&orm, len * 8));
   CU(cudaMemcpyAsync(cm, B, len * 8, cudaMemcpyHostToDevice, s.stream));
   launch_transpose(cm, rm, h->n, mcols, mcols, 0, s.stream);
   launch_spmm(h->n, s.dd.rp, s.dd.ci, s.dd.va, rm, mcols, mcols, orm, mcols, 0, 1.0, nullptr, 0.0, s.stream);
@@ -774,7 +818,7 @@ int bsreg_eval_spmm(bsreg_handle *h, const double *B, int32_t mcols, double *out
   CU(cudaStreamSynchronize(s.stream));
   for (int i = 0; i < h->n; ++i)
     for (int c = 0; c < mcols; ++c) out[(size_t)c * h->n + i] = host[(size_t)i * mcols + c];
-  cudaFree(cm); cudaFree(rm); cudaFree(orm);
+  pool_free(cm); pool_free(rm); pool_free(orm);
   return BSREG_OK;
 }
 
@@ -784,14 +828,14 @@ int bsreg_eval_gram(bsreg_handle *h, double *G) {
   CU(cudaSetDevice(s.dev));
   enqueue_sweep(h, s, s.stream);
   double *dG;
-  CU(cudaMalloc(&dG, (size_t)h->d * h->d * 8));
+  CU(pool_malloc((void **)&dG, (size_t)h->d * h->d * 8));
   s.dd.gcur = (int)((s.seq + 2) % 3);
   launch_gram_to_double(s.dd, dG, s.stream);
   ++h->launches;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(G, dG, (size_t)h->d * h->d * 8, cudaMemcpyDeviceToHost, s.stream));
   CU(cudaStreamSynchronize(s.stream));
-  cudaFree(dG);
+  pool_free(dG);
   return BSREG_OK;
 }
 
@@ -801,8 +845,8 @@ int bsreg_eval_residual_ss(bsreg_handle *h, int32_t n_eval, const double *beta, 
   Shard &s = h->shards[0];
   CU(cudaSetDevice(s.dev));
   double *db, *dl, *dr, *dout, *part;
-  CU(cudaMalloc(&db, (size_t)n_eval * h->m * 8)); CU(cudaMalloc(&dl, (size_t)n_eval * 8)); CU(cudaMalloc(&dr, (size_t)n_eval * 8));
-  CU(cudaMalloc(&dout, (size_t)n_eval * 8)); CU(cudaMalloc(&part, (size_t)592 * 4 * 8));
+  CU(pool_malloc((void **)&db, (size_t)n_eval * h->m * 8)); CU(pool_malloc((void **)&dl, (size_t)n_eval * 8)); CU(pool_malloc((void **)&dr, (size_t)n_eval * 8));
+  CU(pool_malloc((void **)&dout, (size_t)n_eval * 8)); CU(pool_malloc((void **)&part, (size_t)592 * 4 * 8));
   CU(cudaMemcpyAsync(db, beta, (size_t)n_eval * h->m * 8, cudaMemcpyHostToDevice, s.stream));
   CU(cudaMemcpyAsync(dl, lam, (size_t)n_eval * 8, cudaMemcpyHostToDevice, s.stream));
   CU(cudaMemcpyAsync(dr, rho, (size_t)n_eval * 8, cudaMemcpyHostToDevice, s.stream));
@@ -811,7 +855,7 @@ int bsreg_eval_residual_ss(bsreg_handle *h, int32_t n_eval, const double *beta, 
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(ss, dout, (size_t)n_eval * 8, cudaMemcpyDeviceToHost, s.stream));
   CU(cudaStreamSynchronize(s.stream));
-  cudaFree(db); cudaFree(dl); cudaFree(dr); cudaFree(dout); cudaFree(part);
+  pool_free(db); pool_free(dl); pool_free(dr); pool_free(dout); pool_free(part);
   return BSREG_OK;
 }
 
@@ -821,14 +865,14 @@ int bsreg_eval_logdet(bsreg_handle *h, int32_t n_eval, const double *v, double *
   if (s.dd.n_nodes <= 0) return fail(BSREG_EINVAL, "handle has no log-determinant nodes");
   CU(cudaSetDevice(s.dev));
   double *dv, *dout;
-  CU(cudaMalloc(&dv, (size_t)n_eval * 8)); CU(cudaMalloc(&dout, (size_t)n_eval * 8));
+  CU(pool_malloc((void **)&dv, (size_t)n_eval * 8)); CU(pool_malloc((void **)&dout, (size_t)n_eval * 8));
   CU(cudaMemcpyAsync(dv, v, (size_t)n_eval * 8, cudaMemcpyHostToDevice, s.stream));
   launch_eval_logdet(s.dd, n_eval, dv, dout, s.stream);
   ++h->launches;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(ldet, dout, (size_t)n_eval * 8, cudaMemcpyDeviceToHost, s.stream));
   CU(cudaStreamSynchronize(s.stream));
-  cudaFree(dv); cudaFree(dout);
+  pool_free(dv); pool_free(dout);
   return BSREG_OK;
 }
 
@@ -865,7 +909,7 @@ int bsreg_eval_conditionals(bsreg_handle *h, int32_t n_eval, const double *beta,
   CU(cudaSetDevice(s.dev));
   const size_t ne = n_eval, m = h->m;
   double *buf;
-  CU(cudaMalloc(&buf, (ne * m * 3 + ne * 6) * 8));
+  CU(pool_malloc((void **)&buf, (ne * m * 3 + ne * 6) * 8));
   double *db = buf, *dp0 = db + ne * m, *dmu1 = dp0 + ne * m, *ds2 = dmu1 + ne * m, *dl = ds2 + ne, *dv = dl + ne,
          *drate = dv + ne, *drss = drate + ne, *dlp = drss + ne;
   CU(cudaMemcpyAsync(db, beta, ne * m * 8, cudaMemcpyHostToDevice, s.stream));
@@ -882,7 +926,7 @@ int bsreg_eval_conditionals(bsreg_handle *h, int32_t n_eval, const double *beta,
   if (rss) CU(cudaMemcpyAsync(rss, drss, ne * 8, cudaMemcpyDeviceToHost, s.stream));
   if (logpost) CU(cudaMemcpyAsync(logpost, dlp, ne * 8, cudaMemcpyDeviceToHost, s.stream));
   CU(cudaStreamSynchronize(s.stream));
-  cudaFree(buf);
+  pool_free(buf);
   return BSREG_OK;
 }
 
@@ -892,7 +936,7 @@ int bsreg_eval_rng(int32_t kind, uint64_t seed, int32_t chain, int32_t slot, int
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(BSREG_ENOGPU, "no CUDA device available"); }
   double *dp, *dout;
-  CU(cudaMalloc(&dp, 4 * 8)); CU(cudaMalloc(&dout, (size_t)n * 8));
+  CU(pool_malloc((void **)&dp, 4 * 8)); CU(pool_malloc((void **)&dout, (size_t)n * 8));
   double hp[4] = {0, 0, 0, 0};
   const int np = kind == 2 ? 2 : kind == 3 ? 1 : kind == 4 ? 3 : kind == 5 ? 4 : 0;
   for (int i = 0; i < np; ++i) hp[i] = params ? params[i] : 0.0;
@@ -900,7 +944,7 @@ int bsreg_eval_rng(int32_t kind, uint64_t seed, int32_t chain, int32_t slot, int
   launch_eval_rng(kind, seed, chain, slot, it0, n, dp, dout, 0);
   CU(cudaGetLastError());
   CU(cudaMemcpy(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost));
-  cudaFree(dp); cudaFree(dout);
+  pool_free(dp); pool_free(dout);
   return BSREG_OK;
 }
 
@@ -938,5 +982,14 @@ int64_t bsreg_sweep_bytes(const bsreg_handle *h) {
 }
 
 int64_t bsreg_kernel_launches(const bsreg_handle *h) { return h ? h->launches : 0; }
+
+void bsreg_release_cache(void) {
+  std::vector<FreeBlock> drop;
+  { std::lock_guard<std::mutex> lk(g_pool_mu); drop.swap(g_pool_free); g_pool_cached = 0; }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (const FreeBlock &b : drop) { cudaSetDevice(b.dev); cudaFree(b.ptr); }
+  cudaSetDevice(cur);
+}
 
 }  // extern "C"

@@ -86,6 +86,9 @@ bool sweep_fast_supported(const DeviceData &dd);
 bool sweep_ring_supported(int d, int model, int max_blob);   // does the TMA-fed ring sweep cover this design
 void launch_pack_tiles(const double *X, const double *y, double *Zt, int n, int m, cudaStream_t s);
 void launch_gram_to_double(const DeviceData &dd, double *G, cudaStream_t s);
+void launch_pack_csr_tiles(const int *rp, const int *ci, const double *va, const long long *tile_off, unsigned char *blob,
+                           int n, cudaStream_t s);
+void launch_trace_w2_rows(int n, const int *rp, const int *ci, const double *va, double *rowsum, cudaStream_t s);
 void launch_sweep(const DeviceData &dd, int sm_count, cudaStream_t s);
 int  sweep_launch_count();
 void launch_residual_ss(const DeviceData &dd, int n_eval, const double *beta,

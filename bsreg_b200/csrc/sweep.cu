@@ -72,6 +72,45 @@ void launch_pack_tiles(const double *X, const double *y, double *Zt, int n, int 
   pack_tiles_kernel<<<592, 256, 0, s>>>(X, y, Zt, n, m, ntiles);
 }
 
+// per-tile CSR blobs of the ring sweep: {int rp_local[R + 4]; double va[nz~2]; int ci[nz~4]} at tile_off[t]
+__global__ void pack_csr_tiles_kernel(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
+                                      const long long *__restrict__ tile_off, unsigned char *__restrict__ blob, int n) {
+  constexpr int R = SWEEP_TILE_ROWS;
+  const int t = blockIdx.x, r0 = t * R, p0 = rp[r0];
+  unsigned char *b = blob + tile_off[t];
+  int *rpl = reinterpret_cast<int *>(b);
+  for (int i = threadIdx.x; i < R + 4; i += blockDim.x) rpl[i] = i <= R ? rp[min(r0 + i, n)] - p0 : 0;
+  const int nz = rp[min(r0 + R, n)] - p0;
+  double *bva = reinterpret_cast<double *>(b + (R + 4) * 4);
+  int *bci = reinterpret_cast<int *>(bva + ((nz + 1) & ~1));
+  for (int q = threadIdx.x; q < ((nz + 1) & ~1); q += blockDim.x) bva[q] = q < nz ? va[p0 + q] : 0.0;
+  for (int q = threadIdx.x; q < ((nz + 3) & ~3); q += blockDim.x) bci[q] = q < nz ? ci[p0 + q] : 0;
+}
+
+void launch_pack_csr_tiles(const int *rp, const int *ci, const double *va, const long long *tile_off, unsigned char *blob,
+                           int n, cudaStream_t s) {
+  const int ntiles = (n + SWEEP_TILE_ROWS - 1) / SWEEP_TILE_ROWS;
+  pack_csr_tiles_kernel<<<ntiles, 128, 0, s>>>(rp, ci, va, tile_off, blob, n);
+}
+
+// rowsum[i] = sum_p W_ip W_{col[p], i}: tr(W^2) = sum_i rowsum[i] (exact second Chebyshev moment)
+__global__ void trace_w2_rows_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci,
+                                     const double *__restrict__ va, double *__restrict__ rowsum) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int p = rp[i], pe = rp[i + 1]; p < pe; ++p) {
+      const int j = ci[p];
+      for (int q = rp[j], qe = rp[j + 1]; q < qe; ++q)     // no ordering of the column indices is assumed
+        if (ci[q] == i) acc = fma(va[p], va[q], acc);
+    }
+    rowsum[i] = acc;
+  }
+}
+
+void launch_trace_w2_rows(int n, const int *rp, const int *ci, const double *va, double *rowsum, cudaStream_t s) {
+  trace_w2_rows_kernel<<<592, 256, 0, s>>>(n, rp, ci, va, rowsum);
+}
+
 // fixed-point accumulator -> symmetric double matrix (parity entry point bsreg_eval_gram)
 __global__ void gram_to_double_kernel(DeviceData dd, double *G) {
   const int d = dd.d;
@@ -748,7 +787,7 @@ __global__ void __launch_bounds__(256) dot_kernel(const double *__restrict__ a, 
   __shared__ double red[8];
   double acc = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
-    acc = fma(a[i], b[i], acc);
+    acc = b ? fma(a[i], b[i], acc) : acc + a[i];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();

@@ -165,6 +165,10 @@ int  bsreg_sync(bsreg_handle *h);
 int64_t bsreg_sweep_bytes(const bsreg_handle *h);            /* algorithmic bytes of one sweep, SURVEY.md 8(d) */
 int64_t bsreg_kernel_launches(const bsreg_handle *h);        /* kernels launched so far by this handle */
 
+/* Device buffers of destroyed handles are cached for the next bsreg_create (R sessions call bm() repeatedly;
+ * cudaMalloc/cudaFree dominate a short fit otherwise).  This returns the cache to the driver. */
+void bsreg_release_cache(void);
+
 #ifdef __cplusplus
 }
 #endif
