@@ -13,7 +13,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB = ROOT / "lib" / "libbsreg_cuda.so"
-SOURCES = ["api.cu", "sweep.cu", "chain.cu"]
+SOURCES = ["api.cu", "sweep.cu", "chain.cu", "persist.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -41,6 +41,8 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     objdir.mkdir(exist_ok=True)
     nvcc = _nvcc()
     extra = ["-DBSREG_TRACE"] if os.environ.get("BSREG_TRACE") else []   # clock64 trace points (diagnostics)
+    if os.environ.get("BSREG_CHAINS_PER_CTA"):                            # tuning knob of the persistent kernel
+        extra.append("-DBSREG_CHAINS_PER_CTA=" + os.environ["BSREG_CHAINS_PER_CTA"])
 
     def compile_one(src: str):
         obj = objdir / (src[:-3] + ".o")

@@ -130,6 +130,7 @@ struct Shard {
   ChainState cs{};
   std::vector<void *> allocs;
   RunCtl *ctl_dev = nullptr;
+  void *psync = nullptr;              // counters of the persistent kernel
   double *draws_dev = nullptr;
   int save_cap = 0;
   double *p0_init = nullptr, *beta0 = nullptr;
@@ -225,8 +226,18 @@ int build_graph(bsreg_handle *h, Shard &s) {
   return BSREG_OK;
 }
 
-int enqueue_iterations(bsreg_handle *h, Shard &s, int count) {
+int enqueue_iterations(bsreg_handle *h, Shard &s, int count, const RunCtl &ctl) {
   const bool streamed = h->stats_mode == BSREG_STATS_STREAM;
+  if (streamed && count >= 3 && persistent_supported(s.dd, h->pr, s.cs.n_chains, s.sm_count)) {
+    // one cooperative launch for the whole block: sweep CTAs and chain CTAs meet at the triple-buffered Gram matrix
+    const size_t gbytes = (size_t)3 * h->d * h->d * 8;
+    CU(cudaMemsetAsync(s.dd.Gfix, 0, gbytes, s.stream));
+    CU(cudaMemsetAsync(s.psync, 0, persistent_sync_bytes(), s.stream));
+    CU(launch_persistent(s.dd, h->pr, s.cs, ctl, s.draws_dev, count, s.psync, s.sm_count, s.stream));
+    s.seq = 3 + count % 3;            // the last Gram matrix is in buffer (count - 1) % 3, buffer count % 3 is clear
+    h->launches += 1;
+    return BSREG_OK;
+  }
   const int per_iter = streamed ? 2 : 1;
   while (count > 0) {
     if (count >= GRAPH_UNROLL && (!streamed || s.seq % 3 == 0)) {
@@ -493,6 +504,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   TRY(s.alloc(&cs.mh_scale, (size_t)n_chains * 2)); TRY(s.alloc(&cs.mh_cnt, (size_t)n_chains * 8));
   TRY(s.alloc(&cs.iters, (size_t)n_chains)); TRY(s.alloc(&cs.step, (size_t)n_chains));
   TRY(s.alloc(&mu0, (size_t)m)); TRY(s.alloc(&s.p0_init, (size_t)m)); TRY(s.alloc(&s.ctl_dev, 1));
+  { unsigned char *ps; TRY(s.alloc(&ps, persistent_sync_bytes())); s.psync = ps; }
   CU(cudaMemsetAsync(cs.aux, 0, (size_t)n_chains * A * 8, s.stream));
   CU(cudaMemsetAsync(cs.step, 0, (size_t)n_chains * 4, s.stream));
   std::vector<double> hmu(m), hp0(m);
@@ -697,7 +709,7 @@ int bsreg_run(bsreg_handle *h, int32_t n_burn, int32_t n_save, const bsreg_mh *m
       ctl.save_cap = s.save_cap;
       ctl.save_base = saving ? (int)(done - n_burn) : 0;
       CU(cudaMemcpyAsync(s.ctl_dev, &ctl, sizeof ctl, cudaMemcpyHostToDevice, s.stream));
-      TRY(enqueue_iterations(h, s, nb));
+      TRY(enqueue_iterations(h, s, nb, ctl));
       if (saving && draws) {
         double *dst = draws + (size_t)s.chain_lo * h->P * n_save + ctl.save_base;
         CU(cudaMemcpy2DAsync(dst, (size_t)n_save * 8, s.draws_dev, (size_t)s.save_cap * 8, (size_t)nb * 8,

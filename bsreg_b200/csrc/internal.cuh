@@ -110,6 +110,12 @@ struct ChainInit {
 void launch_chain_init(const DeviceData &dd, const Priors &pr, const ChainState &cs, const ChainInit &ci, cudaStream_t s);
 void launch_chain_step(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl *ctl, double *draws,
                        cudaStream_t s);
+// launchers (persist.cu)
+bool persistent_supported(const DeviceData &dd, const Priors &pr, int n_chains, int sm_count);
+size_t persistent_sync_bytes();
+cudaError_t launch_persistent(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl &ctl, double *draws,
+                              int K, void *sync, int sm_count, cudaStream_t s);
+
 void launch_eval_logdet(const DeviceData &dd, int n_eval, const double *v, double *out, cudaStream_t s);
 void launch_eval_conditionals(const DeviceData &dd, const Priors &pr, const double *mu0, int n_eval, const double *beta,
                               const double *sigma2, const double *lam, const double *p0, const double *v, double *mu1,

@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "internal.cuh"
+#include "ring.cuh"
 #include "rng.cuh"
 
 namespace bsreg {
@@ -349,74 +350,6 @@ __global__ void __launch_bounds__(SweepCfg<NB>::T) sweep_gram_kernel(DeviceData 
 // 32 (64) lane partials in a fixed order and issues ONE 64-bit fixed-point atomic; there is
 // no finalisation pass -- consumers read the fixed-point buffer (internal.cuh: g_load).
 // ---------------------------------------------------------------------------
-struct BlockMap { unsigned char gi[32], gj[32]; };
-
-// deal the blocks of G to math warps so that the four SM sub-partitions (warp % 4) carry equal DFMA work
-template <int NG>
-constexpr BlockMap make_block_map() {
-  constexpr int NBLK = NG * (NG + 1) / 2;
-  BlockMap bm{};
-  int gi[32] = {}, gj[32] = {}, nb = 0;
-  for (int i = 0; i < NG; ++i) for (int j = i + 1; j < NG; ++j) { gi[nb] = i; gj[nb] = j; ++nb; }   // 36 FMAs per row
-  for (int i = 0; i < NG; ++i) { gi[nb] = i; gj[nb] = i; ++nb; }                                       // 21 FMAs per row
-  int load[4] = {0, 0, 0, 0}, used[32] = {};
-  for (int b = 0; b < nb; ++b) {
-    int best = -1;
-    for (int w = 0; w < NBLK; ++w) {
-      if (used[w]) continue;
-      if (best < 0 || load[w % 4] < load[best % 4]) best = w;
-    }
-    used[best] = 1;
-    load[best % 4] += (gi[b] == gj[b]) ? 21 : 36;
-    bm.gi[best] = (unsigned char)gi[b];
-    bm.gj[best] = (unsigned char)gj[b];
-  }
-  return bm;
-}
-template <int NG> __constant__ BlockMap c_block_map = make_block_map<NG>();
-
-template <int NG>
-struct Ring {
-  static constexpr int NBLK = NG * (NG + 1) / 2;
-  static constexpr int WPB = (NBLK >= 8) ? 1 : 2;                    // math warps per block of G (row split)
-  static constexpr int MATH = NBLK * WPB;
-  static constexpr int MATHW = (MATH + 3) / 4 * 4;                    // roles are aligned to warpgroups (setmaxnreg)
-  static constexpr int GATHER = 7;                                    // gather warps = tiles whose lag is in flight
-  static constexpr int T = (MATHW + GATHER + 1) * 32;                // gather warps + the producer warp = 2 warpgroups
-  // setmaxnreg moves registers inside the CTA's own allocation (T x the launch-bound count, 96 here):
-  // MATHW * 32 * REG_MATH + 8 * 32 * REG_LIGHT must not exceed it
-  static constexpr int REG_MATH = 120, REG_LIGHT = 56;
-  static_assert(MATHW * 32 * REG_MATH + 8 * 32 * REG_LIGHT <= T * 96, "register pool");
-  static constexpr int R = SWEEP_TILE_ROWS;                          // rows per tile
-  static constexpr int NC = 6 * NG;                                   // tile columns incl. zero padding
-  static constexpr int NRED = NBLK * 36;                              // entries reduced in the tail
-  static constexpr size_t RED_BYTES = (size_t)NRED * (WPB * 32 + 1) * 8;
-};
-constexpr int RING_MAX_STAGES = 12;
-constexpr size_t RING_SMEM_BUDGET = 200 * 1024;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *b, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 template <int NG>
 __global__ void __launch_bounds__(Ring<NG>::T, 1)
 sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes) {
@@ -616,17 +549,7 @@ __global__ void gram_generic_kernel(DeviceData dd) {
 bool sweep_fast_supported(const DeviceData &dd) { return dd.d <= 88; }
 
 // ring geometry for a given design: stages that fit the shared-memory budget (0 = use the other paths)
-int sweep_ring_stage_bytes(int d, int max_blob) { return d <= 24 ? 6 * ((d + 5) / 6) * SWEEP_TILE_ROWS * 8 + max_blob : 0; }
-static int ring_stages(int d, int max_blob) {
-  const int sb = sweep_ring_stage_bytes(d, max_blob);
-  if (sb == 0) return 0;
-  int S = (int)(RING_SMEM_BUDGET / sb);
-  if (S > RING_MAX_STAGES) S = RING_MAX_STAGES;
-  static const int cap = getenv("BSREG_RING_STAGES") ? atoi(getenv("BSREG_RING_STAGES")) : 0;   // tuning knob
-  if (cap >= 3 && S > cap) S = cap;
-  return S >= 3 ? S : 0;
-}
-bool sweep_ring_supported(int d, int model, int max_blob) { return model != 2 && ring_stages(d, max_blob) > 0; }
+bool sweep_ring_supported(int d, int model, int max_blob) { return ring_supported_impl(d, model, max_blob); }
 
 template <int NG>
 static void launch_sweep_ring(const DeviceData &dd, int sm_count, cudaStream_t s) {

@@ -190,3 +190,38 @@ def test_chebyshev_moments_and_nodes():
         assert np.max(np.abs(got - same_input) / np.maximum(np.abs(same_input), 1.0)) < 1e-8
         exact = np.array([core.ldet_dense(t, p.W) for t in v])     # approximation error, reported separately
         assert np.max(np.abs(got - exact)) < 0.05 * len(p.y) ** 0.5
+
+
+# ---------------------------------------------------------------------------
+# persistent kernel (csrc/persist.cu): used for Independent-prior LM / SAR with 13 <= d <= 24
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("model,k", [("sar", 12), ("sar", 20), ("lm", 14), ("sar", 22)])
+def test_persistent_kernel_trajectories(model, k):
+    """Several chains per chain CTA, sweeps running ahead on the other SMs: every chain must still
+    reproduce the oracle chain of its global id, burn-in tuning and continuation included."""
+    p = small_problem(model, n=3000, k=k, knn=7)
+    n_burn, n_save, n_chains, off = 40, 50, 6, 2
+    with cuda_handle(model, p, seed=123, n_chains=n_chains, chain_offset=off) as h:
+        a = h.run(n_burn, 30)
+        b = h.run(0, n_save - 30)                                   # second launch continues on-chip state
+        got = np.concatenate([a, b], axis=2)
+        st = h.get_state()
+    assert st["iterations"].tolist() == [n_burn + n_save] * n_chains
+    for c in (0, 3, 5):
+        ref = oracle_draws(oracle_chain(model, p, seed=123, chain=off + c), n_save, n_burn)
+        assert relnorm(got[c].T, ref) < 1e-7, (model, k, c)
+
+
+def test_persistent_equals_cached_statistics_path():
+    """Stream mode (persistent kernel, Gram matrix rebuilt every iteration) and cached mode (one sweep,
+    one launch per chain step) see the same Gram matrix bit for bit and run the same schedule; the
+    two kernels are compiled separately, so draws agree to rounding, not bit for bit."""
+    from bsreg_b200 import capi
+    p = small_problem("sar", n=2500, k=16, knn=6)
+    with cuda_handle("sar", p, seed=9, n_chains=5) as h:
+        s = h.run(30, 25)
+        G = h.eval_gram()
+    with cuda_handle("sar", p, seed=9, n_chains=5, stats_mode=capi.STATS_CACHED) as h:
+        c = h.run(30, 25)
+        assert np.array_equal(G, h.eval_gram())
+    assert relnorm(s, c) < 1e-9
