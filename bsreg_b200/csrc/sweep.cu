@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(SweepCfg<NB>::T) sweep_gram_kernel(DeviceData 
 // ---------------------------------------------------------------------------
 template <int NG>
 __global__ void __launch_bounds__(Ring<NG>::T, 1)
-sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes) {
+sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, int yg_off, int dbg) {
   using C = Ring<NG>;
   const BlockMap &bm = c_block_map<NG>;
   constexpr int T = C::T, R = C::R, NC = C::NC, WPB = C::WPB, MATH = C::MATH, MATHW = C::MATHW, GATHER = C::GATHER, NRED = C::NRED;
@@ -431,37 +431,13 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes) {
     // =========================== gather: Wy of the tile ===========================
     // one warp per tile, GATHER tiles in flight; lane -> rows lane, lane + 32; the first GU
     // nonzeros of both rows are gathered with every load in flight, longer rows finish serially
-    constexpr int GU = 10;
     // a waiter may be at most one phase away from its barrier: never more gather warps than stages
     const int g = wid - MATHW, ng = S < GATHER ? S : GATHER;
     int s = g;
     uint32_t ph = 0;
     for (int j = g; j < (g < ng ? my_tiles : 0); j += ng) {
       mbar_wait(&full[s], ph);
-      if (has_w) {
-        double *Z = stZ(s);
-        const int *RP = reinterpret_cast<const int *>(stC(s));
-        const int nz = RP[R];
-        const double *VA = reinterpret_cast<const double *>(stC(s) + (R + 4) * 4);
-        const int *CI = reinterpret_cast<const int *>(VA + ((nz + 1) & ~1));
-        int pb[R / 32], pe[R / 32];
-        double yv[R / 32][GU];
-#pragma unroll
-        for (int hh = 0; hh < R / 32; ++hh) {
-          pb[hh] = RP[lane + 32 * hh]; pe[hh] = RP[lane + 32 * hh + 1];
-#pragma unroll
-          for (int u = 0; u < GU; ++u) yv[hh][u] = pb[hh] + u < pe[hh] ? __ldg(yg + CI[pb[hh] + u]) : 0.0;
-        }
-#pragma unroll
-        for (int hh = 0; hh < R / 32; ++hh) {
-          double a = 0.0;                                             // CSR order, fused multiply-add (as K1)
-#pragma unroll
-          for (int u = 0; u < GU; ++u) if (pb[hh] + u < pe[hh]) a = fma(VA[pb[hh] + u], yv[hh][u], a);
-          for (int p = pb[hh] + GU; p < pe[hh]; ++p) a = fma(VA[p], __ldg(yg + CI[p]), a);
-          Z[(m + 1) * R + lane + 32 * hh] = a;
-        }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); // generic writes before the stage is refilled
-      }
+      if (has_w && !(dbg & 4)) ring_gather_tile(stZ(s), stC(s), reinterpret_cast<double *>(stC(s) + yg_off), yg, m, lane);
       __syncwarp();
       if (lane == 0) mbar_arrive(&lag[s]);
       s += ng;
@@ -484,6 +460,7 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes) {
     for (int j = 0; j < (wid < MATH ? my_tiles : 0); ++j) {
       mbar_wait(&lag[s], ph);
       const double *Z = stZ(s);
+      if (!(dbg & 2))
 #pragma unroll
       for (int rr = 0; rr < (R / 32) / WPB; ++rr) {
         const int r = lane + 32 * (wr + WPB * rr);
@@ -564,7 +541,8 @@ static void launch_sweep_ring(const DeviceData &dd, int sm_count, cudaStream_t s
   }
   const int ntiles = (dd.n + C::R - 1) / C::R;
   const int grid = ntiles < sm_count ? ntiles : sm_count;
-  sweep_ring_kernel<NG><<<grid, C::T, smem, s>>>(dd, ntiles, S, sb);
+  static const int dbg = getenv("BSREG_DBG") ? atoi(getenv("BSREG_DBG")) : 0;   // ablation switches (profiling only)
+  sweep_ring_kernel<NG><<<grid, C::T, smem, s>>>(dd, ntiles, S, sb, ring_yg_offset(dd.d, dd.tile_max_blob) - C::NC * C::R * 8, dbg);
 }
 
 template <int NB>

@@ -1,8 +1,7 @@
 #!/bin/bash
-for n in 2000 100000; do
-  for m in lm sar; do
-    for dbg in 0 1 2 4 8 9 15; do
-      echo -n "dbg=$dbg "; BSREG_DBG=$dbg python profiles/run_sweep_only.py $m $n 300
-    done
+# ablation of the standalone ring sweep: 0 full, 2 no math, 4 no gather, 6 neither (TMA streaming only)
+for n in 100000 1000000; do
+  for dbg in 0 2 4 6; do
+    echo -n "dbg=$dbg "; BSREG_DBG=$dbg timeout 60 python profiles/run_sweep_only.py sar $n 240
   done
 done
