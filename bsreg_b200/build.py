@@ -33,11 +33,13 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
+def build_library(force: bool = False, verbose: bool = False, variant: str = "") -> Path:
+    """variant: suffix of a side build (lib/libbsreg_cuda_<variant>.so, own object directory) for A/B profiling."""
+    if not variant and not force and not needs_build():
         return LIB
     LIB.parent.mkdir(exist_ok=True)
-    objdir = ROOT / "lib" / "obj"
+    objdir = ROOT / "lib" / ("obj_" + variant if variant else "obj")
+    out = LIB.with_name(f"libbsreg_cuda_{variant}.so") if variant else LIB
     objdir.mkdir(exist_ok=True)
     nvcc = _nvcc()
     extra = ["-DBSREG_TRACE"] if os.environ.get("BSREG_TRACE") else []   # clock64 trace points (diagnostics)
@@ -57,12 +59,13 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", str(out), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    print(build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=var[0] if var else ""))

@@ -11,7 +11,10 @@ from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libbsreg_cuda.so"
+import os
+
+# BSREG_CUDA_LIB selects another build of the same library (profiling variants); the default is the in-tree build
+LIB_PATH = Path(os.environ.get("BSREG_CUDA_LIB") or Path(__file__).resolve().parent / "lib" / "libbsreg_cuda.so")
 
 MODEL_LM, MODEL_SAR, MODEL_SEM = 0, 1, 2
 PRIOR_INDEPENDENT, PRIOR_CONJUGATE, PRIOR_SHRINKAGE, PRIOR_HORSESHOE = 0, 1, 2, 3

@@ -234,7 +234,10 @@ int enqueue_iterations(bsreg_handle *h, Shard &s, int count, const RunCtl &ctl) 
     CU(cudaMemsetAsync(s.dd.Gfix, 0, gbytes, s.stream));
     CU(cudaMemsetAsync(s.psync, 0, persistent_sync_bytes(), s.stream));
     CU(launch_persistent(s.dd, h->pr, s.cs, ctl, s.draws_dev, count, s.psync, s.sm_count, s.stream));
-    s.seq = 3 + count % 3;            // the last Gram matrix is in buffer (count - 1) % 3, buffer count % 3 is clear
+    // the last Gram matrix is in buffer (count - 1) % 3; the other two were consumed but not recycled: clear them
+    for (int k = 0; k < 2; ++k)
+      CU(cudaMemsetAsync(s.dd.Gfix + (size_t)((count + k) % 3) * h->d * h->d, 0, gbytes / 3, s.stream));
+    s.seq = 3 + count % 3;
     h->launches += 1;
     return BSREG_OK;
   }

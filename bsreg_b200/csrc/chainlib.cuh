@@ -270,7 +270,7 @@ struct InitArgs {
 
 
 #ifdef BSREG_TRACE
-static __device__ long long g_trace[32];
+static __device__ long long g_trace[64];
 #define TRACE(i) do { if (blockIdx.x == 0 && tid == 0) g_trace[i] = clock64(); } while (0)
 #else
 #define TRACE(i) do { } while (0)
