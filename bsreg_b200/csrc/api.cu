@@ -366,6 +366,39 @@ int set_nodes(bsreg_handle *h) {
   return BSREG_OK;
 }
 
+// Does W lack locality?  (share of nonzeros further than max(1024, n/64) from the diagonal above 20 %: e.g. points in
+// random order; a panel's block-diagonal kronecker W or spatially sorted observations stay as they are)
+static bool wants_reorder(int n, const int *rp, const int *ci) {
+  static const char *env = getenv("BSREG_REORDER");                  // A/B switch: 0 = never, 1 = always
+  if (env) return atoi(env) != 0;
+  if (n < 4096) return false;
+  const long long far = std::max(1024, n / 64);
+  long long cnt = 0, tot = 0;
+  const int step = std::max(1, n / 8192);                             // a sample of the rows is enough
+  for (int i = 0; i < n; i += step)
+    for (int q = rp[i]; q < rp[i + 1]; ++q) { ++tot; cnt += std::llabs((long long)ci[q] - i) > far; }
+  return tot > 0 && cnt * 5 > tot;
+}
+
+// Breadth-first relabelling over the out-edges of W (queue order, restarted at the smallest unvisited observation):
+// consecutive labels are graph neighbours of neighbours, so the rows of a 64-row tile share most of their columns.
+static void bfs_order(int n, const int *rp, const int *ci, std::vector<int> &perm) {
+  perm.resize(n);
+  std::vector<unsigned char> seen(n, 0);
+  int head = 0, tail = 0;
+  for (int root = 0; root < n; ++root) {
+    if (seen[root]) continue;
+    seen[root] = 1; perm[tail++] = root;
+    while (head < tail) {
+      const int v = perm[head++];
+      for (int q = rp[v]; q < rp[v + 1]; ++q) {
+        const int u = ci[q];
+        if (!seen[u]) { seen[u] = 1; perm[tail++] = u; }
+      }
+    }
+  }
+}
+
 int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_options *o, int n_chains, int chain_lo) {
   CU(cudaSetDevice(s.dev));
   CU(cudaDeviceGetAttribute(&s.sm_count, cudaDevAttrMultiProcessorCount, s.dev));   // (cudaGetDeviceProperties costs milliseconds)
@@ -424,36 +457,65 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   h->launches += 1;
   pt.mark("y, X upload + transpose");
   // ---- tile-blocked operands of the ring sweep (sweep.cu): Zt and the per-tile CSR blobs ----
-  dd.Zt = nullptr; dd.csr_blob = nullptr; dd.tile_off = nullptr; dd.tile_max_blob = 0;
+  dd.Zt = nullptr; dd.csr_blob = nullptr; dd.tile_off = nullptr; dd.tile_len = nullptr; dd.yp = y;
+  dd.tile_max_blob = 0; dd.tile_max_nu = 0;
   {
     constexpr int R = SWEEP_TILE_ROWS;
     const int ntiles = (n + R - 1) / R;
-    std::vector<long long> off(ntiles + 1, 0);
-    int max_blob = 0;
     const bool with_w = h->model != BSREG_MODEL_LM;
+    // internal ordering of the observations (the Gram matrix does not depend on it): breadth-first when W has no locality
+    std::vector<int> perm;
+    if (with_w && d <= 24 && wants_reorder(n, p->row_ptr, p->col_idx)) bfs_order(n, p->row_ptr, p->col_idx, perm);
+    const bool permuted = !perm.empty();
+    std::vector<long long> off(ntiles + 1, 0);
+    int cap_blob = 0, cap_nu = 0;
     if (with_w) {
       for (int t = 0; t < ntiles; ++t) {
-        const int r0 = t * R, p0 = p->row_ptr[r0];
-        const int nz = p->row_ptr[std::min(r0 + R, n)] - p0;
-        off[t + 1] = off[t] + (R + 4) * 4 + (long long)((nz + 1) & ~1) * 8 + (long long)((nz + 3) & ~3) * 4;
-        max_blob = std::max<long long>(max_blob, off[t + 1] - off[t]);
+        int nz = 0;
+        if (permuted) {
+          for (int r = t * R; r < std::min(t * R + R, n); ++r) nz += p->row_ptr[perm[r] + 1] - p->row_ptr[perm[r]];
+        } else {
+          nz = p->row_ptr[std::min(t * R + R, n)] - p->row_ptr[t * R];
+        }
+        const int cap = tile_blob_bytes(nz, nz);                     // room for a tile whose columns are all distinct
+        off[t + 1] = off[t] + cap;
+        cap_blob = std::max(cap_blob, cap);
+        cap_nu = std::max(cap_nu, nz);
       }
     }
-    if (sweep_ring_supported(d, h->model, max_blob)) {
-      double *zt;
+    if (sweep_ring_supported(d, h->model, cap_blob, cap_nu)) {
+      double *zt, *yp = nullptr;
+      int *dperm = nullptr, *dinv = nullptr;
+      if (permuted) {
+        std::vector<int> inv(n);
+        for (int r = 0; r < n; ++r) inv[perm[r]] = r;
+        CU(pool_malloc((void **)&dperm, (size_t)n * 4)); CU(pool_malloc((void **)&dinv, (size_t)n * 4));
+        TRY(upload(s, perm.data(), dperm, (size_t)n * 4));
+        TRY(upload(s, inv.data(), dinv, (size_t)n * 4));
+        CU(cudaStreamSynchronize(s.stream));                 // `inv` is a host temporary
+        TRY(s.alloc(&yp, (size_t)n));
+      }
       TRY(s.alloc(&zt, (size_t)ntiles * (m + 1) * R));
-      launch_pack_tiles(X, y, zt, n, m, s.stream);
+      launch_pack_tiles(X, y, dperm, zt, yp, n, m, s.stream);
       h->launches += 1;
       dd.Zt = zt;
+      if (permuted) dd.yp = yp;
       if (with_w) {
-        unsigned char *db; long long *doff;
-        TRY(s.alloc(&db, (size_t)off[ntiles] + 16)); TRY(s.alloc(&doff, (size_t)ntiles + 1));
+        unsigned char *db; long long *doff; int *dlen, *dmax;
+        TRY(s.alloc(&db, (size_t)off[ntiles] + 16)); TRY(s.alloc(&doff, (size_t)ntiles + 1)); TRY(s.alloc(&dlen, (size_t)ntiles + 2));
+        dmax = dlen + ntiles;
+        CU(cudaMemsetAsync(dmax, 0, 8, s.stream));
         TRY(upload(s, off.data(), doff, ((size_t)ntiles + 1) * 8));
-        launch_pack_csr_tiles(rp, ci, va, doff, db, n, s.stream);
+        launch_pack_csr_tiles(rp, ci, va, dperm, dinv, doff, dlen, dmax, db, n, s.stream);
         h->launches += 1;
+        int mx[2] = {0, 0};
+        CU(cudaMemcpyAsync(mx, dmax, 8, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaStreamSynchronize(s.stream));                 // `off` is a host temporary
-        dd.csr_blob = db; dd.tile_off = doff; dd.tile_max_blob = max_blob;
+        dd.csr_blob = db; dd.tile_off = doff; dd.tile_len = dlen; dd.tile_max_blob = mx[0]; dd.tile_max_nu = mx[1];
+      } else {
+        CU(cudaStreamSynchronize(s.stream));
       }
+      if (permuted) { pool_free(dperm); pool_free(dinv); }
     }
   }
 

@@ -16,9 +16,18 @@ namespace bsreg {
 //         j % 3 and clears buffer (j + 1) % 3; the chain step of iteration j reads buffer j % 3,
 //         so sweep j + 1 can overlap chain step j.  value = Gfix * Gscale (power of two).
 //   Zt    ring sweep: [ntiles][m+1][R] tile-blocked copy of [X | y] (column-major inside a tile)
-//   csr_blob / tile_off: per tile {int rp_local[R+4]; double va[nz~2]; int ci[nz~4]}, 16-byte aligned
+//   csr_blob / tile_off / tile_len: per tile {int rp_local[R+1], nu, 2 spare; double va[nz~2]; int ci[nz~4]; int ul[nu~4]},
+//         16-byte aligned: ul = the distinct columns of the tile (ascending), ci indexes ul.  Rows and columns of the
+//         tiles are in the handle's internal ordering (perm: a breadth-first relabelling of the observations made at
+//         create when W has no locality; the Gram matrix does not depend on the order of the observations); yp = y in
+//         that ordering.  Everything else (rp/ci/va, X, y, Wy, WX) stays in the caller's ordering.
 // ---------------------------------------------------------------------------
 constexpr int SWEEP_TILE_ROWS = 64;
+
+// bytes of a tile's blob: header {rp_local[R + 1], nu, 2 spare}, va[nz~2], ci[nz~4] (indices into ul), ul[nu~4]
+__host__ __device__ inline int tile_blob_bytes(int nz, int nu) {
+  return ((SWEEP_TILE_ROWS + 4) * 4 + ((nz + 1) & ~1) * 8 + ((nz + 3) & ~3) * 4 + ((nu + 3) & ~3) * 4 + 15) & ~15;
+}
 
 struct DeviceData {
   int n, m, d, model;
@@ -28,8 +37,11 @@ struct DeviceData {
   const double *y, *X;
   const double *Zt;           // ring sweep: tile-blocked [X | y] (null: design not covered by the ring)
   const unsigned char *csr_blob;
-  const long long *tile_off;  // ntiles + 1 byte offsets into csr_blob
-  int tile_max_blob;          // largest blob of one tile (bytes)
+  const long long *tile_off;  // ntiles + 1 byte offsets into csr_blob (capacity of each tile)
+  const int *tile_len;        // ntiles: bytes of each tile's blob actually used (what the ring copies)
+  const double *yp;           // y in the ordering of the tiles
+  int tile_max_blob;          // largest used blob of one tile (bytes)
+  int tile_max_nu;            // most distinct columns in one tile
   double *Wy, *WX;            // cached lags (R/15_sar.R:57, R/15_sem.R:63-64): direct-form kernel, generic sweep
   long long *Gfix;            // 3 * d*d
   int gcur, gzero;            // buffer this launch accumulates into / reads; buffer a sweep clears (-1: none)
@@ -83,11 +95,11 @@ void launch_spmm(int n, const int *rp, const int *ci, const double *va, const do
                  double *out, int ldo, int col0, double alpha, const double *C, double beta, cudaStream_t s);
 void launch_colnorms(const DeviceData &dd, double *norms, cudaStream_t s);
 bool sweep_fast_supported(const DeviceData &dd);
-bool sweep_ring_supported(int d, int model, int max_blob);   // does the TMA-fed ring sweep cover this design
-void launch_pack_tiles(const double *X, const double *y, double *Zt, int n, int m, cudaStream_t s);
+bool sweep_ring_supported(int d, int model, int max_blob, int max_nu);   // does the TMA-fed ring sweep cover this design
+void launch_pack_tiles(const double *X, const double *y, const int *perm, double *Zt, double *yp, int n, int m, cudaStream_t s);
 void launch_gram_to_double(const DeviceData &dd, double *G, cudaStream_t s);
-void launch_pack_csr_tiles(const int *rp, const int *ci, const double *va, const long long *tile_off, unsigned char *blob,
-                           int n, cudaStream_t s);
+void launch_pack_csr_tiles(const int *rp, const int *ci, const double *va, const int *perm, const int *inv,
+                           const long long *tile_off, int *tile_len, int *max_len_nu, unsigned char *blob, int n, cudaStream_t s);
 void launch_trace_w2_rows(int n, const int *rp, const int *ci, const double *va, double *rowsum, cudaStream_t s);
 void launch_sweep(const DeviceData &dd, int sm_count, cudaStream_t s);
 int  sweep_launch_count();

@@ -52,9 +52,10 @@ void launch_transpose(const double *src, double *dst, int n, int m, int ld, int 
   transpose_kernel<<<grid, block, 0, s>>>(src, dst, n, m, ld, col0);
 }
 
-// Zt[tile][c][r] for the ring sweep: columns X_1..X_m then y, zero padded to whole tiles
-__global__ void pack_tiles_kernel(const double *__restrict__ X, const double *__restrict__ y, double *__restrict__ Zt,
-                                  int n, int m, int ntiles) {
+// Zt[tile][c][r] for the ring sweep: columns X_1..X_m then y, zero padded to whole tiles; tile row r is observation
+// perm[r] (perm == null: the caller's order); yp = y in the same order (the gather source of the ring)
+__global__ void pack_tiles_kernel(const double *__restrict__ X, const double *__restrict__ y, const int *__restrict__ perm,
+                                  double *__restrict__ Zt, double *__restrict__ yp, int n, int m, int ntiles) {
   constexpr int R = SWEEP_TILE_ROWS;
   const size_t total = (size_t)ntiles * (m + 1) * R;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -63,35 +64,129 @@ __global__ void pack_tiles_kernel(const double *__restrict__ X, const double *__
     const int c = (int)(tc % (m + 1)), tile = (int)(tc / (m + 1));
     const int row = tile * R + r;
     double v = 0.0;
-    if (row < n) v = c < m ? X[(size_t)row * m + c] : y[row];
+    if (row < n) {
+      const int src = perm ? perm[row] : row;
+      v = c < m ? X[(size_t)src * m + c] : y[src];
+      if (c == m && yp != nullptr) yp[row] = v;
+    }
     Zt[idx] = v;
   }
 }
 
-void launch_pack_tiles(const double *X, const double *y, double *Zt, int n, int m, cudaStream_t s) {
+void launch_pack_tiles(const double *X, const double *y, const int *perm, double *Zt, double *yp, int n, int m, cudaStream_t s) {
   const int ntiles = (n + SWEEP_TILE_ROWS - 1) / SWEEP_TILE_ROWS;
-  pack_tiles_kernel<<<592, 256, 0, s>>>(X, y, Zt, n, m, ntiles);
+  pack_tiles_kernel<<<592, 256, 0, s>>>(X, y, perm, Zt, yp, n, m, ntiles);
 }
 
-// per-tile CSR blobs of the ring sweep: {int rp_local[R + 4]; double va[nz~2]; int ci[nz~4]} at tile_off[t]
-__global__ void pack_csr_tiles_kernel(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
-                                      const long long *__restrict__ tile_off, unsigned char *__restrict__ blob, int n) {
+// per-tile CSR blobs of the ring sweep (layout: tile_blob_bytes in ring.cuh).  One CTA per tile: rows perm[r0..r0+R) of the
+// caller's CSR, columns relabelled by inv; the entries of a row keep their order (Wy is summed as K1 sums it).  The
+// distinct columns of the tile are found by a bitonic sort in shared memory; tiles with more than PACK_CAP nonzeros
+// are written without de-duplication (ul = the columns as they come).
+constexpr int PACK_CAP = 4096, PACK_T = 256;
+__global__ void __launch_bounds__(PACK_T) pack_csr_tiles_kernel(const int *__restrict__ rp, const int *__restrict__ ci,
+                                                                const double *__restrict__ va, const int *__restrict__ perm,
+                                                                const int *__restrict__ inv, const long long *__restrict__ tile_off,
+                                                                int *__restrict__ tile_len, int *__restrict__ max_len_nu,
+                                                                unsigned char *__restrict__ blob, int n) {
   constexpr int R = SWEEP_TILE_ROWS;
-  const int t = blockIdx.x, r0 = t * R, p0 = rp[r0];
+  __shared__ int rpl[R + 1], src0[R];
+  __shared__ int keys[PACK_CAP];
+  __shared__ int s_nu;
+  const int t = blockIdx.x, r0 = t * R, tid = threadIdx.x;
+  if (tid == 0) {
+    int acc = 0;
+    for (int i = 0; i < R; ++i) {
+      rpl[i] = acc;
+      const int row = r0 + i;
+      if (row < n) {
+        const int src = perm ? perm[row] : row;
+        src0[i] = rp[src];
+        acc += rp[src + 1] - rp[src];
+      } else {
+        src0[i] = 0;
+      }
+    }
+    rpl[R] = acc;
+  }
+  __syncthreads();
+  const int nz = rpl[R];
   unsigned char *b = blob + tile_off[t];
-  int *rpl = reinterpret_cast<int *>(b);
-  for (int i = threadIdx.x; i < R + 4; i += blockDim.x) rpl[i] = i <= R ? rp[min(r0 + i, n)] - p0 : 0;
-  const int nz = rp[min(r0 + R, n)] - p0;
+  int *hdr = reinterpret_cast<int *>(b);
   double *bva = reinterpret_cast<double *>(b + (R + 4) * 4);
   int *bci = reinterpret_cast<int *>(bva + ((nz + 1) & ~1));
-  for (int q = threadIdx.x; q < ((nz + 1) & ~1); q += blockDim.x) bva[q] = q < nz ? va[p0 + q] : 0.0;
-  for (int q = threadIdx.x; q < ((nz + 3) & ~3); q += blockDim.x) bci[q] = q < nz ? ci[p0 + q] : 0;
+  int *bul = bci + ((nz + 3) & ~3);
+  // values, and the relabelled columns (into bci for now)
+  for (int i = tid / 32; i < R; i += PACK_T / 32) {
+    const int len = rpl[i + 1] - rpl[i];
+    for (int q = tid % 32; q < len; q += 32) {
+      const int c = ci[src0[i] + q];
+      bva[rpl[i] + q] = va[src0[i] + q];
+      bci[rpl[i] + q] = inv ? inv[c] : c;
+    }
+  }
+  for (int q = nz + tid; q < ((nz + 1) & ~1); q += PACK_T) bva[q] = 0.0;
+  __syncthreads();
+  int nu = nz;
+  if (nz <= PACK_CAP) {
+    int np2 = 1;
+    while (np2 < nz) np2 <<= 1;
+    for (int q = tid; q < np2; q += PACK_T) keys[q] = q < nz ? bci[q] : 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int q = tid; q < np2; q += PACK_T) {
+          const int l = q ^ j;
+          if (l > q) {
+            const int a = keys[q], c = keys[l];
+            const bool up = (q & k) == 0;
+            if ((a > c) == up) { keys[q] = c; keys[l] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    // distinct keys, compacted in place by one warp (ballot scan), ascending
+    if (tid < 32) {
+      int base = 0;
+      for (int q0 = 0; q0 < nz; q0 += 32) {
+        const int q = q0 + tid;
+        const int kq = q < nz ? keys[q] : 0;
+        const bool first = q < nz && (q == 0 || keys[q - 1] != kq);
+        const unsigned mask = __ballot_sync(0xffffffffu, first);
+        __syncwarp();
+        if (first) keys[base + __popc(mask & ((1u << tid) - 1))] = kq;   // base + rank <= q: never ahead of the reads
+        base += __popc(mask);
+        __syncwarp();
+      }
+      if (tid == 0) s_nu = base;
+    }
+    __syncthreads();
+    nu = s_nu;
+    for (int q = tid; q < nz; q += PACK_T) {               // column -> position in the distinct list
+      const int c = bci[q];
+      int lo = 0, hi = nu - 1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < c) lo = mid + 1; else hi = mid; }
+      bci[q] = lo;
+    }
+    for (int q = tid; q < ((nu + 3) & ~3); q += PACK_T) bul[q] = q < nu ? keys[q] : 0;
+  } else {
+    for (int q = tid; q < ((nz + 3) & ~3); q += PACK_T) bul[q] = q < nz ? bci[q] : 0;
+    __syncthreads();
+    for (int q = tid; q < nz; q += PACK_T) bci[q] = q;
+  }
+  for (int q = nz + tid; q < ((nz + 3) & ~3); q += PACK_T) bci[q] = 0;
+  for (int i = tid; i < R + 4; i += PACK_T) hdr[i] = i <= R ? rpl[i] : (i == R + 1 ? nu : 0);
+  if (tid == 0) {
+    const int len = tile_blob_bytes(nz, nu);
+    tile_len[t] = len;
+    atomicMax(&max_len_nu[0], len);
+    atomicMax(&max_len_nu[1], nu);
+  }
 }
 
-void launch_pack_csr_tiles(const int *rp, const int *ci, const double *va, const long long *tile_off, unsigned char *blob,
-                           int n, cudaStream_t s) {
+void launch_pack_csr_tiles(const int *rp, const int *ci, const double *va, const int *perm, const int *inv,
+                           const long long *tile_off, int *tile_len, int *max_len_nu, unsigned char *blob, int n, cudaStream_t s) {
   const int ntiles = (n + SWEEP_TILE_ROWS - 1) / SWEEP_TILE_ROWS;
-  pack_csr_tiles_kernel<<<ntiles, 128, 0, s>>>(rp, ci, va, tile_off, blob, n);
+  pack_csr_tiles_kernel<<<ntiles, PACK_T, 0, s>>>(rp, ci, va, perm, inv, tile_off, tile_len, max_len_nu, blob, n);
 }
 
 // rowsum[i] = sum_p W_ip W_{col[p], i}: tr(W^2) = sum_i rowsum[i] (exact second Chebyshev moment)
@@ -361,7 +456,7 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, int yg_off,
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int m = dd.m, d = dd.d;
   const bool has_w = dd.model != 0;
-  const double *__restrict__ yg = dd.y;
+  const double *__restrict__ yg = dd.yp;
 
   // the accumulator of the sweep after next: its last reader finished before this launch
   if (blockIdx.x == 0 && dd.gzero >= 0) {
@@ -411,14 +506,16 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, int yg_off,
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 1;                                                // fresh barriers: the "previous" phase is complete
-      long long o0 = 0, o1 = 0;
-      if (has_w && my_tiles > 0) { o0 = dd.tile_off[blockIdx.x]; o1 = dd.tile_off[blockIdx.x + 1]; }
+      long long o0 = 0;
+      int o1 = 0;
+      if (has_w && my_tiles > 0) { o0 = dd.tile_off[blockIdx.x]; o1 = dd.tile_len[blockIdx.x]; }
       for (int j = 0; j < my_tiles; ++j) {
         const int tile = blockIdx.x + j * gridDim.x;
-        long long n0 = 0, n1 = 0;                                     // next tile's blob range, fetched early
-        if (has_w && j + 1 < my_tiles) { n0 = dd.tile_off[tile + gridDim.x]; n1 = dd.tile_off[tile + gridDim.x + 1]; }
+        long long n0 = 0;                                             // next tile's blob, fetched early
+        int n1 = 0;
+        if (has_w && j + 1 < my_tiles) { n0 = dd.tile_off[tile + gridDim.x]; n1 = dd.tile_len[tile + gridDim.x]; }
         mbar_wait(&empty[s], ph);
-        const uint32_t c_bytes = (uint32_t)(o1 - o0);
+        const uint32_t c_bytes = (uint32_t)o1;
         mbar_expect_tx(&full[s], z_bytes + c_bytes);
         tma_bulk_g2s(stZ(s), dd.Zt + (size_t)tile * (m + 1) * R, z_bytes, &full[s]);
         if (c_bytes) tma_bulk_g2s(stC(s), dd.csr_blob + o0, c_bytes, &full[s]);
@@ -526,12 +623,12 @@ __global__ void gram_generic_kernel(DeviceData dd) {
 bool sweep_fast_supported(const DeviceData &dd) { return dd.d <= 88; }
 
 // ring geometry for a given design: stages that fit the shared-memory budget (0 = use the other paths)
-bool sweep_ring_supported(int d, int model, int max_blob) { return ring_supported_impl(d, model, max_blob); }
+bool sweep_ring_supported(int d, int model, int max_blob, int max_nu) { return ring_supported_impl(d, model, max_blob, max_nu); }
 
 template <int NG>
 static void launch_sweep_ring(const DeviceData &dd, int sm_count, cudaStream_t s) {
   using C = Ring<NG>;
-  const int S = ring_stages(dd.d, dd.tile_max_blob), sb = sweep_ring_stage_bytes(dd.d, dd.tile_max_blob);
+  const int S = ring_stages(dd.d, dd.tile_max_blob, dd.tile_max_nu), sb = sweep_ring_stage_bytes(dd.d, dd.tile_max_blob, dd.tile_max_nu);
   size_t smem = (size_t)S * sb;
   if (smem < C::RED_BYTES) smem = C::RED_BYTES;
   static size_t configured = 0;

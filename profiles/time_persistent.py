@@ -1,5 +1,6 @@
 """Per-iteration time of the persistent Gibbs kernel for a few (N, chains): separates the chain-step latency
 (N tiny) from the streaming time (few chains)."""
+import os
 import sys
 import time
 from pathlib import Path
@@ -12,7 +13,7 @@ cases = [(2000, 64), (100_000, 4), (100_000, 64), (100_000, 128), (1_000_000, 64
 if len(sys.argv) > 1:
     cases = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
 for n, chains in cases:
-    p = make_problem("sar", n=n, k_reg=20, knn=10)
+    p = make_problem("sar", n=n, k_reg=20, knn=10, sort=bool(os.environ.get("BSREG_SORT")))
     with capi.Handle(p.y, p.X, model=capi.MODEL_SAR, W=p.W, ldet=capi.LDET_CHEBYSHEV, cheb_order=50, cheb_probes=16,
                      n_chains=chains, seed=1) as h:
         h.run(2000, 0)                      # warm-up long enough for the clocks to settle
