@@ -369,8 +369,8 @@ int set_nodes(bsreg_handle *h) {
 // Does W lack locality?  (share of nonzeros further than max(1024, n/64) from the diagonal above 20 %: e.g. points in
 // random order; a panel's block-diagonal kronecker W or spatially sorted observations stay as they are)
 static bool wants_reorder(int n, const int *rp, const int *ci) {
-  static const char *env = getenv("BSREG_REORDER");                  // A/B switch: 0 = never, 1 = always
-  if (env) return atoi(env) != 0;
+  const char *env = getenv("BSREG_REORDER");                         // A/B switch: 0 = never, 1 = always (read per create)
+  if (env && *env) return atoi(env) != 0;
   if (n < 4096) return false;
   const long long far = std::max(1024, n / 64);
   long long cnt = 0, tot = 0;

@@ -5,6 +5,7 @@ import pytest
 
 from oracle import core
 from oracle.philox import Slot, Stream
+from bsreg_b200.synthetic import make_problem
 from tests.helpers import cuda_handle, oracle_chain, oracle_draws, small_problem
 
 pytestmark = pytest.mark.gpu
@@ -225,3 +226,75 @@ def test_persistent_equals_cached_statistics_path():
         c = h.run(30, 25)
         assert np.array_equal(G, h.eval_gram())
     assert relnorm(s, c) < 1e-9
+
+
+# ---------------------------------------------------------------------------
+# internal ordering of the observations (breadth-first relabelling at create) and per-tile distinct-column lists
+# ---------------------------------------------------------------------------
+def _scrambled(model, n, k, knn, seed=3):
+    """A problem whose observations are in random order (no locality in W): triggers the relabelling."""
+    from bsreg_b200.synthetic import Problem
+    p = make_problem(model, n=n, k_reg=k, knn=knn, sort=True)
+    q = np.random.default_rng(seed).permutation(n)
+    W = p.W[q][:, q].tocsr()
+    W.sort_indices()
+    W.indices = W.indices.astype(np.int32)
+    W.indptr = W.indptr.astype(np.int32)
+    return Problem(p.y[q].copy(), np.ascontiguousarray(p.X[q]), W, p.beta, p.sigma, p.lam, p.model, p.coords[q])
+
+
+@pytest.mark.parametrize("n", [4200, 9001])
+def test_gram_is_invariant_to_internal_ordering(n, monkeypatch):
+    """Z'Z does not depend on the order of the observations: the sweep over relabelled, de-duplicated tiles must give the
+    oracle's Gram matrix, and the same one (to rounding) with the relabelling switched off or forced on."""
+    p = _scrambled("sar", n, 9, 8)
+    Wy = core.spmm(p.W, p.y)
+    G_ref = core.gram(p.y, p.X, Wy, None)
+    scale = np.sqrt(np.outer(np.diag(G_ref), np.diag(G_ref)))
+    got = {}
+    for mode in ("", "0", "1"):
+        monkeypatch.setenv("BSREG_REORDER", mode)
+        with cuda_handle("sar", p, ldet=capi_mod().LDET_CHEBYSHEV, cheb_order=8, cheb_probes=4) as h:
+            got[mode] = h.eval_gram()
+            assert relnorm(h.eval_spmm(p.y[:, None])[:, 0], Wy) < 1e-13     # K1 stays in the caller's ordering
+        assert np.max(np.abs(got[mode] - G_ref) / scale) < 1e-13, mode
+    assert np.max(np.abs(got["0"] - got["1"]) / scale) < 1e-14
+
+
+def test_chains_are_invariant_to_internal_ordering(monkeypatch):
+    """Same draws (to rounding) with and without the relabelling, persistent kernel included (d = 16)."""
+    p = _scrambled("sar", 5000, 14, 7)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("BSREG_REORDER", mode)
+        with cuda_handle("sar", p, seed=21, n_chains=5, ldet=capi_mod().LDET_CHEBYSHEV, cheb_order=20, cheb_probes=8) as h:
+            out[mode] = h.run(30, 30)
+    assert relnorm(out["0"], out["1"]) < 1e-9
+
+
+def test_tiles_with_long_and_empty_rows(monkeypatch):
+    """Ragged W: empty rows and one very long row (a tile with 1800 nonzeros: three ring stages of 56 KB)."""
+    import scipy.sparse as sp
+    n = 4500
+    rng = np.random.default_rng(5)
+    p = make_problem("sar", n=n, k_reg=6, knn=5)
+    W = p.W.tolil()
+    for i in (0, 63, 64, 1000, n - 1):
+        W.rows[i] = []; W.data[i] = []
+    cols = np.sort(rng.choice(n, 1500, replace=False))
+    W.rows[2000] = cols.tolist(); W.data[2000] = (np.full(1500, 1.0 / 1500)).tolist()
+    W = sp.csr_matrix(W)
+    W.indices = W.indices.astype(np.int32); W.indptr = W.indptr.astype(np.int32)
+    Wy = core.spmm(W, p.y)
+    G_ref = core.gram(p.y, p.X, Wy, None)
+    scale = np.sqrt(np.outer(np.diag(G_ref), np.diag(G_ref)))
+    for mode in ("0", "1"):
+        monkeypatch.setenv("BSREG_REORDER", mode)
+        with capi_mod().Handle(p.y, p.X, model=capi_mod().MODEL_SAR, W=W, ldet=capi_mod().LDET_CHEBYSHEV, cheb_order=6,
+                               cheb_probes=2, n_chains=1, seed=1) as h:
+            assert np.max(np.abs(h.eval_gram() - G_ref) / scale) < 1e-13, mode
+
+
+def capi_mod():
+    from bsreg_b200 import capi
+    return capi
