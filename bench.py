@@ -36,6 +36,11 @@ CHEB_ORDER, CHEB_PROBES = 50, 64
 ITERS_PER_STEP = 500
 E2E_BURN, E2E_SAVE = 500, 1000           # defaults of bm(), R/60_interface.R:39
 METRIC = "SAR Gibbs chain-iter/s at N=100k, 64 chains/GPU"
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the persistent kernel (500 iterations), from the
+# `ncu --set full` capture summarised in profiles/ (None until a capture of the current kernel is committed)
+NCU_DRAM_BYTES_PER_LAUNCH = 31842048 + 0
+NCU_TRAFFIC_SOURCE = ("ncu dram__bytes_read.sum + dram__bytes_write.sum of one 500-iteration launch "
+                      "(profiles/r1_persistent_final_dram_bytes.csv); full capture: profiles/r1_persistent_final_ncu_full.txt")
 
 
 def load_peaks():
@@ -278,7 +283,9 @@ def run_ours(args):
             tot += a.elapsed_time(b)
         return tot / reps
 
-    roof = cpu = e2e = None
+    roof = cpu = e2e = big = None
+    if rank == 0 and not args.skip_big:
+        big = hbm_resident_check(capi, torch, hbm_peak)
     if rank == 0:
         sweep_warm = time_launches(h.launch_sweep, 400, False)
         sweep_cold = time_launches(h.launch_sweep, 20, True)
@@ -290,11 +297,16 @@ def run_ours(args):
         roof = {"kernel": "gibbs_persistent_kernel<4>: 132 sweep CTAs (TMA-fed fused CSR SpMV + Gram reduction, one "
                           "pass over W, y, X per Gibbs iteration) + 16 chain CTAs, one cooperative launch per step",
                 "bound": "hbm", "achieved": in_loop, "peak": hbm_peak, "unit": "GB/s", "frac": in_loop / hbm_peak,
-                "traffic": None, "algorithmic_bytes": bytes_sweep * ITERS_PER_STEP,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE,
+                "algorithmic_bytes": bytes_sweep * ITERS_PER_STEP,
                 "algorithmic_bytes_per_iteration": bytes_sweep, "peak_source": peak_src,
                 "launch_us": step_ms * 1e3, "iterations_per_launch": ITERS_PER_STEP,
-                "note": "in-loop: operands L2-resident after the first iteration (29 MB working set, same every "
-                        "iteration); the iteration time is set by the per-chain step latency, not by the stream",
+                "note": "in-loop: the 29 MB of operands are L2-resident after the first iteration (same operands every "
+                        "iteration), so DRAM traffic per launch is one pass, not iterations_per_launch passes; the "
+                        "algorithmic figure is W, y, X streamed once per Gibbs iteration (SURVEY 8d).  The sweep CTAs and "
+                        "the chain CTAs are balanced (sweep-bound and chain-bound times within 15 % of each other); "
+                        "hbm_resident_check runs the same kernel at N = 1e6, where the operands (292 MB) exceed L2",
+                "hbm_resident_check": big,
                 "sweep_alone": {"kernel": "sweep_ring_kernel<4>, one launch per sweep on 148 SMs", "launch_us": sweep_warm * 1e3,
                                 "achieved": alone, "frac": alone / hbm_peak,
                                 "cold": {"launch_us": sweep_cold * 1e3, "achieved": bytes_sweep / (sweep_cold * 1e-3) / 1e9,
@@ -335,9 +347,11 @@ def run_ours(args):
         # bounded CPU sample on this box's host cores
         cores = os.cpu_count() or 1
         procs = max(1, min(cores, CHAINS_PER_GPU))
-        cpu_val, cpu_wall = cpu_throughput(p, cpu_nodes(p), 40, procs)
+        nodes_cpu = cpu_nodes(p)
+        cpu_iters = 40 if args.skip_cpu else 2000                                # about 12-15 s of CPU work on every core used
+        cpu_val, cpu_wall = cpu_throughput(p, nodes_cpu, cpu_iters, procs)
         cpu = {"value": cpu_val, "unit": "chain-iter/s", "cores": procs, "kind": "port",
-               "sample": f"{procs} chains x 40 iterations ({cpu_wall:.1f} s), one single-threaded process per chain",
+               "sample": f"{procs} chains x {cpu_iters} iterations ({cpu_wall:.1f} s), one single-threaded process per chain",
                "note": "reference-algorithm CPU restatement (NumPy/SciPy), not R; R is not installed"}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "chain-iter/s", "n_gpus": world, "steps": args.steps,
@@ -353,6 +367,26 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def hbm_resident_check(capi, torch, hbm_peak):
+    """The same persistent kernel at N = 1e6 (SAR, K = 20, 64 chains): 292 MB of operands per iteration do not fit the
+    126 MB L2, so every iteration streams them from HBM."""
+    p = make_cfg4(1_000_000)
+    with capi.Handle(p.y, p.X, model=capi.MODEL_SAR, W=p.W, ldet=capi.LDET_CHEBYSHEV, cheb_order=CHEB_ORDER,
+                     cheb_probes=8, n_chains=CHAINS_PER_GPU, seed=5) as hb:
+        st = torch.cuda.ExternalStream(hb.stream())
+        hb.run_into(0, 100, None, None)
+        torch.cuda.synchronize()
+        iters = 200
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st); hb.run_into(0, iters, None, None); b.record(st)
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        gbs = hb.sweep_bytes() * iters / (ms * 1e-3) / 1e9
+        return {"workload": "synthetic SAR, N=1000000, kNN(k=10), K=20, 64 chains", "us_per_iteration": 1e3 * ms / iters,
+                "algorithmic_bytes_per_iteration": hb.sweep_bytes(), "achieved": gbs, "unit": "GB/s", "frac": gbs / hbm_peak,
+                "value": CHAINS_PER_GPU * iters / (ms * 1e-3)}
+
+
 def h_bytes_per_chain_iter(bytes_sweep):
     return bytes_sweep / CHAINS_PER_GPU
 
@@ -363,6 +397,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-big", action="store_true", help="skip the N = 1e6 HBM-resident check (saves ~25 s)")
+    ap.add_argument("--skip-cpu", action="store_true", help="shrink the CPU baseline sample to 40 iterations (profiler runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
