@@ -287,56 +287,91 @@ int enqueue_repeated(bsreg_handle *h, Shard &s, int reps, bool sweep) {
   return BSREG_OK;
 }
 
-int trace_moments_dev(bsreg_handle *h, Shard &s, const bsreg_problem *prob_csr, int order, int probes, uint64_t seed,
-                      double *moments) {
+// Chebyshev / Hutchinson trace moments, in two halves so that bsreg_create can run the device work on
+// the auxiliary stream beside the upload of y and X, the relabelling and the tile packing: launch() only enqueues,
+// finish() waits for the results.
+struct MomentsJob {
+  bool active = false;
+  int order = 0, probes = 0;
+  double m1 = 0.0;
+  double *U = nullptr, *buf[3] = {nullptr, nullptr, nullptr}, *res = nullptr, *rowsum = nullptr, *scratch = nullptr;
+  double *host = nullptr;             // pinned: res[0 .. order], then tr(W^2) partial at [order + 1]
+  cudaEvent_t done = nullptr;
+};
+
+int trace_moments_launch(bsreg_handle *h, Shard &s, const bsreg_problem *prob_csr, int order, int probes, uint64_t seed,
+                         MomentsJob &job, cudaStream_t st) {
   const int n = h->n;
-  for (int j = 0; j <= order; ++j) moments[j] = 0.0;
-  moments[0] = n;
+  job.order = order; job.probes = probes; job.active = true;
+  CU(cudaSetDevice(s.dev));
+  CU(cudaMallocHost((void **)&job.host, (size_t)(order + 2) * 8));
+  for (int j = 0; j <= order + 1; ++j) job.host[j] = 0.0;
+  CU(cudaEventCreateWithFlags(&job.done, cudaEventDisableTiming));
+  CU(pool_malloc((void **)&job.res, (size_t)(order + 2) * 8));
+  CU(pool_malloc((void **)&job.scratch, 4096 * 8));
+  if (order >= 2) {   // tr(W^2) = sum_ij W_ij W_ji, exact from the CSR on the device
+    CU(pool_malloc((void **)&job.rowsum, (size_t)n * 8));
+    launch_trace_w2_rows(n, s.dd.rp, s.dd.ci, s.dd.va, job.rowsum, st);
+    launch_dot(job.rowsum, nullptr, n, job.scratch, job.res + order + 1, st);
+    h->launches += 3;
+  }
+  if (order >= 3) {
+    const size_t len = (size_t)n * probes;
+    CU(pool_malloc((void **)&job.U, len * 8));
+    for (int b = 0; b < 3; ++b) CU(pool_malloc((void **)&job.buf[b], len * 8));
+    launch_probes(job.U, n, probes, seed, st);
+    // T_1 = W U ; T_j = 2 W T_{j-1} - T_{j-2}; U stays intact for the dots u'T_j u
+    launch_spmm(n, s.dd.rp, s.dd.ci, s.dd.va, job.U, probes, probes, job.buf[0], probes, 0, 1.0, nullptr, 0.0, st);
+    h->launches += 2;
+    const double *prev = job.U;
+    double *cur = job.buf[0];
+    int nxt = 1;
+    for (int j = 2; j <= order; ++j) {
+      double *next = job.buf[nxt];
+      launch_spmm(n, s.dd.rp, s.dd.ci, s.dd.va, cur, probes, probes, next, probes, 0, 2.0, prev, -1.0, st);
+      ++h->launches;
+      if (j >= 3) { launch_dot(job.U, next, (int64_t)len, job.scratch, job.res + j, st); h->launches += 2; }
+      prev = cur; cur = next; nxt = (nxt + 1) % 3;
+    }
+  }
+  CU(cudaMemcpyAsync(job.host, job.res, (size_t)(order + 2) * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(job.done, st));
+  // tr(W) on the host while the device works
   if (order >= 1) {
     long double tr = 0.0L;
     for (int i = 0; i < n; ++i)
       for (int p = prob_csr->row_ptr[i]; p < prob_csr->row_ptr[i + 1]; ++p)
         if (prob_csr->col_idx[p] == i) tr += prob_csr->val[p];
-    moments[1] = (double)tr;
+    job.m1 = (double)tr;
   }
-  CU(cudaSetDevice(s.dev));
-  if (order >= 2) {   // tr(W^2) = sum_ij W_ij W_ji, exact from the CSR on the device
-    double *rowsum = nullptr, *tw2 = nullptr, host_tw2 = 0.0;
-    CU(pool_malloc((void **)&rowsum, (size_t)n * 8)); CU(pool_malloc((void **)&tw2, 8));
-    launch_trace_w2_rows(n, s.dd.rp, s.dd.ci, s.dd.va, rowsum, s.stream);
-    launch_dot(rowsum, nullptr, n, s.scratch, tw2, s.stream);
-    h->launches += 3;
-    CU(cudaMemcpyAsync(&host_tw2, tw2, 8, cudaMemcpyDeviceToHost, s.stream));
-    CU(cudaStreamSynchronize(s.stream));
-    pool_free(rowsum); pool_free(tw2);
-    moments[2] = 2.0 * host_tw2 - n;
-  }
-  if (order < 3) return BSREG_OK;
-  const size_t len = (size_t)n * probes;
-  double *U = nullptr, *buf[3] = {nullptr, nullptr, nullptr}, *res = nullptr;
-  CU(pool_malloc((void **)&U, len * 8));
-  for (int b = 0; b < 3; ++b) CU(pool_malloc((void **)&buf[b], len * 8));
-  CU(pool_malloc((void **)&res, (order + 1) * 8));
-  launch_probes(U, n, probes, seed, s.stream);
-  // T_1 = W U ; T_j = 2 W T_{j-1} - T_{j-2}; U stays intact for the dots u'T_j u
-  launch_spmm(n, s.dd.rp, s.dd.ci, s.dd.va, U, probes, probes, buf[0], probes, 0, 1.0, nullptr, 0.0, s.stream);
-  h->launches += 2;
-  const double *prev = U;
-  double *cur = buf[0];
-  int nxt = 1;
-  for (int j = 2; j <= order; ++j) {
-    double *next = buf[nxt];
-    launch_spmm(n, s.dd.rp, s.dd.ci, s.dd.va, cur, probes, probes, next, probes, 0, 2.0, prev, -1.0, s.stream);
-    ++h->launches;
-    if (j >= 3) { launch_dot(U, next, (int64_t)len, s.scratch, res + j, s.stream); h->launches += 2; }
-    prev = cur; cur = next; nxt = (nxt + 1) % 3;
-  }
-  std::vector<double> host(order + 1);
-  CU(cudaMemcpyAsync(host.data(), res, (order + 1) * 8, cudaMemcpyDeviceToHost, s.stream));
-  CU(cudaStreamSynchronize(s.stream));
-  for (int j = 3; j <= order; ++j) moments[j] = host[j] / probes;
-  pool_free(U); pool_free(buf[0]); pool_free(buf[1]); pool_free(buf[2]); pool_free(res);
   return BSREG_OK;
+}
+
+int trace_moments_finish(bsreg_handle *h, Shard &s, MomentsJob &job, double *moments) {
+  if (!job.active) return BSREG_OK;
+  const int order = job.order, n = h->n;
+  CU(cudaSetDevice(s.dev));
+  CU(cudaEventSynchronize(job.done));
+  for (int j = 0; j <= order; ++j) moments[j] = 0.0;
+  moments[0] = n;
+  if (order >= 1) moments[1] = job.m1;
+  if (order >= 2) moments[2] = 2.0 * job.host[order + 1] - n;
+  for (int j = 3; j <= order; ++j) moments[j] = job.host[j] / job.probes;
+  if (job.U) pool_free(job.U);
+  for (int b = 0; b < 3; ++b) if (job.buf[b]) pool_free(job.buf[b]);
+  if (job.rowsum) pool_free(job.rowsum);
+  pool_free(job.res); pool_free(job.scratch);
+  cudaFreeHost(job.host);
+  cudaEventDestroy(job.done);
+  job = MomentsJob();
+  return BSREG_OK;
+}
+
+int trace_moments_dev(bsreg_handle *h, Shard &s, const bsreg_problem *prob_csr, int order, int probes, uint64_t seed,
+                      double *moments) {
+  MomentsJob job;
+  TRY(trace_moments_launch(h, s, prob_csr, order, probes, seed, job, s.stream));
+  return trace_moments_finish(h, s, job, moments);
 }
 
 void chebyshev_nodes(const std::vector<double> &mom, int n, std::vector<double> &re, std::vector<double> &im,
@@ -399,7 +434,8 @@ static void bfs_order(int n, const int *rp, const int *ci, std::vector<int> &per
   }
 }
 
-int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_options *o, int n_chains, int chain_lo) {
+int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_options *o, int n_chains, int chain_lo,
+                MomentsJob *moments_job) {
   CU(cudaSetDevice(s.dev));
   CU(cudaDeviceGetAttribute(&s.sm_count, cudaDevAttrMultiProcessorCount, s.dev));   // (cudaGetDeviceProperties costs milliseconds)
   if (o->stream && h->shards.size() == 1) { s.stream = (cudaStream_t)o->stream; s.own_stream = false; }
@@ -424,6 +460,16 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
     TRY(upload(s, p->val, va, (size_t)p->nnz * 8));
   }
   dd.rp = rp; dd.ci = ci; dd.va = va;
+  if (moments_job != nullptr && p->nnz > 0) {
+    // the trace moments need W only: their device work runs on the auxiliary stream beside the rest of the setup
+    cudaEvent_t w_up;
+    CU(cudaEventCreateWithFlags(&w_up, cudaEventDisableTiming));
+    CU(cudaEventRecord(w_up, s.stream));
+    CU(cudaStreamWaitEvent(s.aux, w_up, 0));
+    CU(cudaEventDestroy(w_up));
+    const int order = o->cheb_order > 0 ? o->cheb_order : 50, probes = o->cheb_probes > 0 ? o->cheb_probes : 64;
+    TRY(trace_moments_launch(h, s, p, order, probes, o->seed, *moments_job, s.aux));
+  }
 
   pt.mark("W upload");
   // ---- y, X (column-major on the host -> row-major [n][m] in HBM) ----
@@ -663,12 +709,14 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
   if (ndev > o->n_chains) { delete h; return fail(BSREG_EINVAL, "more devices than chains"); }
   h->shards.resize(ndev);
   int rc = BSREG_OK, lo = 0;
+  MomentsJob mjob;
+  const bool want_moments = h->spatial && o->ldet != BSREG_LDET_NODES;
   for (int g = 0; g < ndev && rc == BSREG_OK; ++g) {
     Shard &s = h->shards[g];
     s.dev = o->n_devices > 0 && o->devices ? o->devices[g] : cur;
     if (s.dev < 0 || s.dev >= ndev_avail) { rc = fail(BSREG_EINVAL, "device %d not available", s.dev); break; }
     const int cnt = o->n_chains / ndev + (g < o->n_chains % ndev ? 1 : 0);   // contiguous blocks of chain ids
-    rc = setup_shard(h, s, p, o, cnt, lo);
+    rc = setup_shard(h, s, p, o, cnt, lo, g == 0 && want_moments ? &mjob : nullptr);
     lo += cnt;
   }
   pt.mark("shards total");
@@ -681,11 +729,13 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
     } else {
       const int order = o->cheb_order > 0 ? o->cheb_order : 50, probes = o->cheb_probes > 0 ? o->cheb_probes : 64;
       std::vector<double> mom(order + 1);
-      rc = trace_moments_dev(h, h->shards[0], p, order, probes, o->seed, mom.data());
+      if (mjob.active) rc = trace_moments_finish(h, h->shards[0], mjob, mom.data());
+      else rc = trace_moments_dev(h, h->shards[0], p, order, probes, o->seed, mom.data());
       if (rc == BSREG_OK) chebyshev_nodes(mom, h->n, h->node_re, h->node_im, h->node_w);
     }
     if (rc == BSREG_OK) rc = set_nodes(h);
   }
+  if (mjob.active) { std::vector<double> drop(mjob.order + 1); trace_moments_finish(h, h->shards[0], mjob, drop.data()); }   // error paths
   pt.mark("log-det nodes");
   if (rc == BSREG_OK) rc = init_chains(h, false);
   pt.mark("chain init");
