@@ -85,6 +85,7 @@ SYMBOLS = {
     "bsreg_sweep_bytes": (C.c_int64, [C.c_void_p]),
     "bsreg_kernel_launches": (C.c_int64, [C.c_void_p]),
     "bsreg_release_cache": (None, []),
+    "bsreg_debug_internal_order": (C.c_int, [C.c_int32, c_ip, c_ip, C.c_int32, c_ip]),
 }
 
 _lib = None

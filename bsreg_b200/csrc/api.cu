@@ -745,6 +745,17 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
   return BSREG_OK;
 }
 
+// Host-side ordering logic of bsreg_create, exposed for the CPU test-suite (no device needed): returns 1 and fills
+// perm[n] (internal row r = caller's observation perm[r]) if W would be relabelled, 0 if it is local enough already.
+int bsreg_debug_internal_order(int32_t n, const int32_t *row_ptr, const int32_t *col_idx, int32_t force, int32_t *perm) {
+  if (n <= 0 || !row_ptr || !col_idx || !perm) return fail(BSREG_EINVAL, "bsreg_debug_internal_order: bad arguments");
+  if (!force && !wants_reorder(n, row_ptr, col_idx)) return 0;
+  std::vector<int> pv;
+  bfs_order(n, row_ptr, col_idx, pv);
+  for (int i = 0; i < n; ++i) perm[i] = pv[i];
+  return 1;
+}
+
 void bsreg_destroy(bsreg_handle *h) {
   if (!h) return;
   int cur = 0;

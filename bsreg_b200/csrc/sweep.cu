@@ -739,12 +739,16 @@ __global__ void __launch_bounds__(256) residual_ss_kernel(DeviceData dd, int e0,
   }
 }
 
+// out[e] = sum over the CTAs' partials, one warp per entry: lane l adds parts l, l + 32, ... in order, then a fixed
+// shuffle tree -- the same order on every run
 __global__ void combine_partials_kernel(const double *partial, int nparts, int stride, int count, double *out) {
-  const int e = threadIdx.x;
+  const int e = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (e < count) {
     double s = 0.0;
-    for (int b = 0; b < nparts; ++b) s += partial[(size_t)b * stride + e];
-    out[e] = s;
+    for (int b = lane; b < nparts; b += 32) s += partial[(size_t)b * stride + e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[e] = s;
   }
 }
 
@@ -753,7 +757,7 @@ void launch_residual_ss(const DeviceData &dd, int n_eval, const double *beta,
   for (int e0 = 0; e0 < n_eval; e0 += RSS_EC) {
     residual_ss_kernel<<<RSS_GRID, 256, RSS_EC * dd.m * sizeof(double), s>>>(dd, e0, n_eval, beta, lam, rho, partial);
     const int ne = n_eval - e0 < RSS_EC ? n_eval - e0 : RSS_EC;
-    combine_partials_kernel<<<1, 32, 0, s>>>(partial, RSS_GRID, RSS_EC, ne, out + e0);
+    combine_partials_kernel<<<1, 32 * RSS_EC, 0, s>>>(partial, RSS_GRID, RSS_EC, ne, out + e0);
   }
 }
 

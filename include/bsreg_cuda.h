@@ -169,6 +169,13 @@ int64_t bsreg_kernel_launches(const bsreg_handle *h);        /* kernels launched
  * cudaMalloc/cudaFree dominate a short fit otherwise).  This returns the cache to the driver. */
 void bsreg_release_cache(void);
 
+/* Host-side logic of bsreg_create that chooses the INTERNAL ordering of the observations for the tiled sweep (the
+ * Gram matrix Z'Z -- everything the sampler needs from N-scale data, R/10_lm.R:36, R/15_sar.R:106-108 -- does not
+ * depend on the order of the rows).  Returns 1 and fills perm[n] (internal row r = caller's observation perm[r],
+ * breadth-first over the out-edges of W) if W has no locality or `force` is set, 0 if W is kept as it is, < 0 on
+ * error.  Needs no device; exists for tests. */
+int bsreg_debug_internal_order(int32_t n, const int32_t *row_ptr, const int32_t *col_idx, int32_t force, int32_t *perm);
+
 #ifdef __cplusplus
 }
 #endif

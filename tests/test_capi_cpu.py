@@ -109,3 +109,54 @@ def test_product_package_never_imports_the_oracle():
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
     code = "import sys; import bsreg_b200, bsreg_b200.capi; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def _order(capi, W, force=0):
+    n = W.shape[0]
+    perm = np.full(n, -1, dtype=np.int32)
+    rp, ci = W.indptr.astype(np.int32), W.indices.astype(np.int32)
+    rc = capi.load().bsreg_debug_internal_order(n, rp.ctypes.data_as(capi.c_ip), ci.ctypes.data_as(capi.c_ip), force,
+                                                perm.ctypes.data_as(capi.c_ip))
+    return rc, perm
+
+
+def test_internal_ordering_of_the_observations(capi):
+    """Host logic of bsreg_create (no device): W without locality is relabelled breadth-first, local W is kept; the
+    relabelling is a permutation that brings the columns of a 64-row tile together."""
+    from bsreg_b200.synthetic import knn_weights
+    n = 20000
+    W_rand, _ = knn_weights(n, 10, 1001, False, False)         # points in random order
+    W_sorted, _ = knn_weights(n, 10, 1001, False, True)        # Morton order: local already
+    rc, perm = _order(capi, W_rand)
+    assert rc == 1
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    rc_s, _ = _order(capi, W_sorted)
+    assert rc_s == 0
+    rc_f, perm_f = _order(capi, W_sorted, force=1)
+    assert rc_f == 1 and np.array_equal(np.sort(perm_f), np.arange(n))
+
+    def distinct_per_tile(W):
+        rp, ci = W.indptr, W.indices
+        return np.mean([len(np.unique(ci[rp[t]:rp[min(t + 64, n)]])) for t in range(0, n, 64)])
+    before = distinct_per_tile(W_rand)
+    Wp = W_rand[perm][:, perm].tocsr()
+    after = distinct_per_tile(Wp)
+    assert before > 600 and after < 0.45 * before               # 640 references per tile, about 220 distinct after
+    # breadth-first queue order: the first observation stays first, its neighbours follow
+    assert perm[0] == 0
+    first = set(W_rand.indices[W_rand.indptr[0]:W_rand.indptr[1]].tolist()) - {0}
+    assert first == set(perm[1:1 + len(first)].tolist())
+
+
+def test_internal_ordering_handles_disconnected_and_empty_rows(capi):
+    import scipy.sparse as sp
+    n = 6000
+    rng = np.random.default_rng(0)
+    rows = np.repeat(np.arange(n), 3)
+    cols = rng.integers(0, n, size=3 * n)
+    A = sp.csr_matrix((np.ones(3 * n), (rows, cols)), shape=(n, n)).tolil()
+    for i in (0, 17, n - 1):
+        A.rows[i] = []; A.data[i] = []
+    A = sp.csr_matrix(A)
+    rc, perm = _order(capi, A, force=1)
+    assert rc == 1 and np.array_equal(np.sort(perm), np.arange(n))
