@@ -322,6 +322,25 @@ class Model:
             out += f", {name} acceptance {mh.get_acceptance():.3f}"
         return out
 
+    def trace_inverse(self, lam):
+        """tr((I - lam W)^-1) for an array of lam, from the SAME spectral nodes the sampler's log-determinant uses
+        (eigenvalues with weight `reps`, or the Chebyshev nodes with weights folded from the Hutchinson trace moments,
+        SURVEY App. B): sum_k w_k Re 1 / (1 - lam omega_k).  Replaces the dense
+        `sum(diag(solve(diag(N) - lambda * W)))` of R/15_sar.R:145-146 (marked "To-do: ... more efficient" there)."""
+        re, im, w = self.handle.nodes()
+        lam = np.atleast_1d(np.asarray(lam, dtype=np.float64))
+        z = 1.0 - lam[:, None] * (re[None, :] + 1j * im[None, :])
+        return np.sum(w[None, :] * (1.0 / z).real, axis=1)
+
+    @property
+    def get_effects(self):
+        """`mdl$get_effects` at the current state of chain 1, R/15_sar.R:143-149 (SAR / SDM only, as in the reference)."""
+        if self.type not in ("sar", "sdm"):
+            raise AttributeError("get_effects is defined for the SAR / SDM models only (R/15_sar.R:143)")
+        p = self.get_parameters
+        m = self.handle.m
+        return effects_from_draws(p[None, :m], p[None, -1:].ravel(), self.trace_inverse(p[-1]) / self.handle.n)
+
     def sample(self, n_save=1000, n_burn=0, mh=None, verbose=True):
         """`sample(mdl, n_save, n_burn, mh, verbose)`, R/50_execute.R:12-42 -- on the device.
         Returns (n_chains, n_save, P)."""
@@ -335,6 +354,14 @@ class Model:
                             (mh["adjust_burn"], mh["acc_target"][0], mh["acc_target"][1], mh["acc_change"]),
                             progress=prog)
         return np.ascontiguousarray(d.transpose(0, 2, 1))
+
+
+def effects_from_draws(beta, lam, tau):
+    """R/15_sar.R:144-148 per draw: total = beta / (1 - lambda), direct = tr((I - lambda W)^-1) / N * beta,
+    indirect = total - direct.  beta (S, M), lam (S,), tau = tr(.)/N (S,)."""
+    total = beta / (1.0 - lam)[:, None]
+    direct = tau[:, None] * beta
+    return {"total": total, "direct": direct, "indirect": total - direct}
 
 
 class BM:
@@ -364,6 +391,16 @@ class BM:
         return {n: dict(zip(("Min.", "1st Qu.", "Median", "Mean", "3rd Qu.", "Max."),
                             (q[0, j], q[1, j], q[2, j], self.draws[:, j].mean(), q[3, j], q[4, j])))
                 for j, n in enumerate(self.colnames)}
+
+    def effects(self, chain=0):
+        """Direct / indirect / total effects of every saved draw of a SAR / SDM fit (what `get_effects`, R/15_sar.R:143-149,
+        gives for one state): dict of (n_save, M) arrays."""
+        if self.model.type not in ("sar", "sdm"):
+            raise AttributeError("effects are defined for the SAR / SDM models only (R/15_sar.R:143)")
+        d = self.chains[chain]
+        m = self.model.handle.m
+        lam = d[:, -1]
+        return effects_from_draws(d[:, :m], lam, self.model.trace_inverse(lam) / self.model.handle.n)
 
     def as_mcmc(self):   # as.mcmc.bm, R/81_coda.R:17-30: the draws matrix with column names
         return self.draws, self.colnames

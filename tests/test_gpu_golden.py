@@ -90,3 +90,41 @@ def test_paper_design_with_fixed_effects(cig, model):
         else:
             rss = core.sem_rss(v[e], y, Wy, X, WX)
         assert abs(got["rss"][e] - rss) / rss < 1e-9
+
+
+def test_spatial_effects_match_the_reference_formula(cig):
+    """`get_effects`, R/15_sar.R:143-149: total = beta / (1 - lambda), direct = tr((I - lambda W)^-1) / N * beta with the
+    reference's dense solve, indirect = total - direct -- here from the spectral nodes, for every saved draw."""
+    cfg = list(configs(cig))[1]                       # bsar on the cigarettes panel (eigenvalue nodes, reps = 30)
+    name, model, prior, pri, y, X, W, X_slx, reps = cfg
+    fit = _fit(cfg, 3, 12, 10)
+    eff = fit.effects()
+    m = X.shape[1]
+    Wd = W.toarray() if hasattr(W, "toarray") else np.asarray(W)
+    n = Wd.shape[0]
+    for s in (0, 5, 11):
+        beta, lam = fit.draws[s, :m], fit.draws[s, -1]
+        direct = np.trace(np.linalg.inv(np.eye(n) - lam * Wd)) / n * beta
+        total = beta / (1.0 - lam)
+        assert np.max(np.abs(eff["direct"][s] - direct)) < 1e-9 * max(1.0, np.max(np.abs(direct)))
+        assert np.max(np.abs(eff["total"][s] - total)) < 1e-12 * max(1.0, np.max(np.abs(total)))
+        assert np.allclose(eff["indirect"][s], total - direct, rtol=0, atol=1e-9)
+    cur = fit.model.get_effects                      # the active binding: current state of chain 1 = the last draw
+    assert np.allclose(cur["direct"][0], eff["direct"][-1]) and np.allclose(cur["total"][0], eff["total"][-1])
+    with pytest.raises(AttributeError):
+        _fit(list(configs(cig))[0], 1, 5, 5).effects()          # blm: no spatial effects in the reference either
+
+
+def test_spatial_effects_from_chebyshev_nodes():
+    """Large-N path: the same quadrature nodes that give log|I - vW| give tr((I - vW)^-1); against a dense inverse."""
+    from bsreg_b200 import capi
+    from bsreg_b200.synthetic import make_problem
+    p = make_problem("sar", n=1500, k_reg=4, knn=6)
+    with capi.Handle(p.y, p.X, model=capi.MODEL_SAR, W=p.W, ldet=capi.LDET_CHEBYSHEV, cheb_order=40, cheb_probes=256,
+                     n_chains=1, seed=3) as h:
+        mdl = bs.interface.Model(h, "sar", "Independent", [], 1)
+        lam = np.array([-0.4, 0.2, 0.6])
+        got = mdl.trace_inverse(lam) / h.n
+    Wd = p.W.toarray()
+    want = np.array([np.trace(np.linalg.inv(np.eye(1500) - v * Wd)) / 1500 for v in lam])
+    assert np.max(np.abs(got - want)) < 5e-3         # Hutchinson error of 256 probes at N = 1500 (exact moments 0-2)
