@@ -497,6 +497,11 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
     if (p->nnz_slx > 0) { pool_free(rps); pool_free(cis); pool_free(vas); }
     h->launches += 2;
   }
+  // internal ordering of the observations for the tiled sweep (the Gram matrix does not depend on it): breadth-first when
+  // W has no locality.  Host work, done here so that it runs beside the uploads and transposes enqueued above.
+  std::vector<int> perm;
+  if (h->model != BSREG_MODEL_LM && d <= 24 && p->nnz > 0 && wants_reorder(n, p->row_ptr, p->col_idx))
+    bfs_order(n, p->row_ptr, p->col_idx, perm);
   CU(cudaStreamSynchronize(s.stream));
   pool_free(tmp);
   dd.y = y; dd.X = X;
@@ -509,21 +514,19 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
     constexpr int R = SWEEP_TILE_ROWS;
     const int ntiles = (n + R - 1) / R;
     const bool with_w = h->model != BSREG_MODEL_LM;
-    // internal ordering of the observations (the Gram matrix does not depend on it): breadth-first when W has no locality
-    std::vector<int> perm;
-    if (with_w && d <= 24 && wants_reorder(n, p->row_ptr, p->col_idx)) bfs_order(n, p->row_ptr, p->col_idx, perm);
-    const bool permuted = !perm.empty();
+    const bool permuted = with_w && !perm.empty();
     std::vector<long long> off(ntiles + 1, 0);
     int cap_blob = 0, cap_nu = 0;
     if (with_w) {
       for (int t = 0; t < ntiles; ++t) {
-        int nz = 0;
-        if (permuted) {
-          for (int r = t * R; r < std::min(t * R + R, n); ++r) nz += p->row_ptr[perm[r] + 1] - p->row_ptr[perm[r]];
-        } else {
-          nz = p->row_ptr[std::min(t * R + R, n)] - p->row_ptr[t * R];
+        int nz = 0, max_len = 0;
+        for (int r = t * R; r < std::min(t * R + R, n); ++r) {
+          const int src = permuted ? perm[r] : r;
+          const int len = p->row_ptr[src + 1] - p->row_ptr[src];
+          nz += len;
+          max_len = std::max(max_len, len);
         }
-        const int cap = tile_blob_bytes(nz, nz);                     // room for a tile whose columns are all distinct
+        const int cap = tile_blob_bytes(nz, nz, ell_width(nz, max_len));   // room for a tile whose columns are all distinct
         off[t + 1] = off[t] + cap;
         cap_blob = std::max(cap_blob, cap);
         cap_nu = std::max(cap_nu, nz);

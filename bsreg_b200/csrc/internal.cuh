@@ -22,11 +22,21 @@ namespace bsreg {
 //         create when W has no locality; the Gram matrix does not depend on the order of the observations); yp = y in
 //         that ordering.  Everything else (rp/ci/va, X, y, Wy, WX) stays in the caller's ordering.
 // ---------------------------------------------------------------------------
+
 constexpr int SWEEP_TILE_ROWS = 64;
 
-// bytes of a tile's blob: header {rp_local[R + 1], nu, 2 spare}, va[nz~2], ci[nz~4] (indices into ul), ul[nu~4]
-__host__ __device__ inline int tile_blob_bytes(int nz, int nu) {
-  return ((SWEEP_TILE_ROWS + 4) * 4 + ((nz + 1) & ~1) * 8 + ((nz + 3) & ~3) * 4 + ((nu + 3) & ~3) * 4 + 15) & ~15;
+// A tile's blob: header {rp_local[R + 1], nu, wt, 1 spare}, values, column slots, ul[nu~4] (the distinct columns).
+//   wt > 0 (rows of similar length, e.g. kNN): slot-major "ELL" layout va[wt][R], ci[wt][R] -- lane = row reads consecutive
+//          addresses, no shared-memory bank conflicts; short rows are padded with (0.0, 0)
+//   wt = 0 (ragged tiles): CSR layout va[nz~2], ci[nz~4]
+// ci indexes ul.  ell_width() is the rule both the host (capacities) and the packing kernel use.
+constexpr int SWEEP_PACK_CAP = 4096;      // nonzeros of a tile the packing kernel sorts (more: CSR layout, no de-duplication)
+__host__ __device__ inline int ell_width(int nz, int max_len) {
+  return (max_len > 0 && nz <= SWEEP_PACK_CAP && SWEEP_TILE_ROWS * max_len <= nz + nz / 4 + SWEEP_TILE_ROWS) ? max_len : 0;
+}
+__host__ __device__ inline int tile_blob_bytes(int nz, int nu, int wt) {
+  const int body = wt > 0 ? wt * SWEEP_TILE_ROWS * 12 : ((nz + 1) & ~1) * 8 + ((nz + 3) & ~3) * 4;
+  return ((SWEEP_TILE_ROWS + 4) * 4 + body + ((nu + 3) & ~3) * 4 + 15) & ~15;
 }
 
 struct DeviceData {

@@ -80,15 +80,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 // fetched once: with observations in a locality-preserving order a 64-row kNN tile (640 nonzeros) has about 200 of them
 // in about 70 sectors.  cp.async (LDGSTS) copies them straight into the stage's Yg area -- no destination registers, so
 // every gather of the tile is in flight at once -- then lane = rows lane, lane + 32 sums each row in CSR order with FMAs
-// (the order of K1), reading Yg through shared memory.
+// (the order of K1), reading Yg through shared memory.  Blob layouts: tile_blob_bytes (internal.cuh).
 __device__ __forceinline__ void ring_gather_tile(double *Z, const unsigned char *C, double *Yg,
                                                  const double *__restrict__ yg, int m, int lane) {
   constexpr int R = SWEEP_TILE_ROWS, GU = 10;
   const int *RP = reinterpret_cast<const int *>(C);
-  const int nz = RP[R], nu = RP[R + 1];
+  const int nz = RP[R], nu = RP[R + 1], wt = RP[R + 2];
   const double *VA = reinterpret_cast<const double *>(C + (R + 4) * 4);
-  const int *CI = reinterpret_cast<const int *>(VA + ((nz + 1) & ~1));
-  const int *UL = CI + ((nz + 3) & ~3);
+  const int *CI = reinterpret_cast<const int *>(VA + (wt > 0 ? wt * R : ((nz + 1) & ~1)));
+  const int *UL = CI + (wt > 0 ? wt * R : ((nz + 3) & ~3));
   for (int t = lane; t < nu; t += 128) {
     int u[4];
 #pragma unroll
@@ -98,23 +98,36 @@ __device__ __forceinline__ void ring_gather_tile(double *Z, const unsigned char 
       if (t + 32 * q < nu)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(Yg + t + 32 * q)), "l"(yg + u[q]) : "memory");
   }
-  int pb[R / 32], pe[R / 32];
+  if (wt > 0) {
+    // slot-major layout: slot u of rows lane, lane + 32 sits at [u][lane], [u][lane + 32] -- consecutive lanes, consecutive
+    // addresses; rows shorter than wt end in (0.0, 0) pairs, which add an exact zero
+    int cl[R / 32][GU];
 #pragma unroll
-  for (int hh = 0; hh < R / 32; ++hh) { pb[hh] = RP[lane + 32 * hh]; pe[hh] = RP[lane + 32 * hh + 1]; }
-  int cl[R / 32][GU];
+    for (int hh = 0; hh < R / 32; ++hh)
 #pragma unroll
-  for (int hh = 0; hh < R / 32; ++hh)
+      for (int u = 0; u < GU; ++u) cl[hh][u] = u < wt ? CI[u * R + lane + 32 * hh] : 0;
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncwarp();
 #pragma unroll
-    for (int u = 0; u < GU; ++u) cl[hh][u] = pb[hh] + u < pe[hh] ? CI[pb[hh] + u] : 0;
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
-  __syncwarp();
+    for (int hh = 0; hh < R / 32; ++hh) {
+      double a = 0.0;
 #pragma unroll
-  for (int hh = 0; hh < R / 32; ++hh) {
-    double a = 0.0;
+      for (int u = 0; u < GU; ++u) if (u < wt) a = fma(VA[u * R + lane + 32 * hh], Yg[cl[hh][u]], a);
+      for (int u = GU; u < wt; ++u) a = fma(VA[u * R + lane + 32 * hh], Yg[CI[u * R + lane + 32 * hh]], a);
+      Z[(m + 1) * R + lane + 32 * hh] = a;
+    }
+  } else {
+    int pb[R / 32], pe[R / 32];
 #pragma unroll
-    for (int u = 0; u < GU; ++u) if (pb[hh] + u < pe[hh]) a = fma(VA[pb[hh] + u], Yg[cl[hh][u]], a);
-    for (int p = pb[hh] + GU; p < pe[hh]; ++p) a = fma(VA[p], Yg[CI[p]], a);
-    Z[(m + 1) * R + lane + 32 * hh] = a;
+    for (int hh = 0; hh < R / 32; ++hh) { pb[hh] = RP[lane + 32 * hh]; pe[hh] = RP[lane + 32 * hh + 1]; }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    __syncwarp();
+#pragma unroll
+    for (int hh = 0; hh < R / 32; ++hh) {
+      double a = 0.0;
+      for (int p = pb[hh]; p < pe[hh]; ++p) a = fma(VA[p], Yg[CI[p]], a);
+      Z[(m + 1) * R + lane + 32 * hh] = a;
+    }
   }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes before the stage is refilled
 }

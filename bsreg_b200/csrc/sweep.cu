@@ -82,7 +82,7 @@ void launch_pack_tiles(const double *X, const double *y, const int *perm, double
 // caller's CSR, columns relabelled by inv; the entries of a row keep their order (Wy is summed as K1 sums it).  The
 // distinct columns of the tile are found by a bitonic sort in shared memory; tiles with more than PACK_CAP nonzeros
 // are written without de-duplication (ul = the columns as they come).
-constexpr int PACK_CAP = 4096, PACK_T = 256;
+constexpr int PACK_CAP = SWEEP_PACK_CAP, PACK_T = 256;
 __global__ void __launch_bounds__(PACK_T) pack_csr_tiles_kernel(const int *__restrict__ rp, const int *__restrict__ ci,
                                                                 const double *__restrict__ va, const int *__restrict__ perm,
                                                                 const int *__restrict__ inv, const long long *__restrict__ tile_off,
@@ -91,10 +91,10 @@ __global__ void __launch_bounds__(PACK_T) pack_csr_tiles_kernel(const int *__res
   constexpr int R = SWEEP_TILE_ROWS;
   __shared__ int rpl[R + 1], src0[R];
   __shared__ int keys[PACK_CAP];
-  __shared__ int s_nu;
+  __shared__ int s_nu, s_maxlen;
   const int t = blockIdx.x, r0 = t * R, tid = threadIdx.x;
   if (tid == 0) {
-    int acc = 0;
+    int acc = 0, mx = 0;
     for (int i = 0; i < R; ++i) {
       rpl[i] = acc;
       const int row = r0 + i;
@@ -102,35 +102,52 @@ __global__ void __launch_bounds__(PACK_T) pack_csr_tiles_kernel(const int *__res
         const int src = perm ? perm[row] : row;
         src0[i] = rp[src];
         acc += rp[src + 1] - rp[src];
+        mx = max(mx, rp[src + 1] - rp[src]);
       } else {
         src0[i] = 0;
       }
     }
     rpl[R] = acc;
+    s_maxlen = mx;
   }
   __syncthreads();
-  const int nz = rpl[R];
+  const int nz = rpl[R], wt = ell_width(nz, s_maxlen);
   unsigned char *b = blob + tile_off[t];
   int *hdr = reinterpret_cast<int *>(b);
   double *bva = reinterpret_cast<double *>(b + (R + 4) * 4);
-  int *bci = reinterpret_cast<int *>(bva + ((nz + 1) & ~1));
-  int *bul = bci + ((nz + 3) & ~3);
+  int *bci = reinterpret_cast<int *>(bva + (wt > 0 ? wt * R : ((nz + 1) & ~1)));
+  int *bul = bci + (wt > 0 ? wt * R : ((nz + 3) & ~3));
+  // position of nonzero q of row i in the blob: slot-major when the tile is regular enough, CSR otherwise
+  auto slot = [&](int i, int q) { return wt > 0 ? q * R + i : rpl[i] + q; };
+  if (wt > 0) for (int e = tid; e < wt * R; e += PACK_T) { bva[e] = 0.0; bci[e] = 0x7fffffff; }   // padding of short rows
+  __syncthreads();
   // values, and the relabelled columns (into bci for now)
   for (int i = tid / 32; i < R; i += PACK_T / 32) {
     const int len = rpl[i + 1] - rpl[i];
     for (int q = tid % 32; q < len; q += 32) {
       const int c = ci[src0[i] + q];
-      bva[rpl[i] + q] = va[src0[i] + q];
-      bci[rpl[i] + q] = inv ? inv[c] : c;
+      bva[slot(i, q)] = va[src0[i] + q];
+      bci[slot(i, q)] = inv ? inv[c] : c;
     }
   }
-  for (int q = nz + tid; q < ((nz + 1) & ~1); q += PACK_T) bva[q] = 0.0;
+  if (wt == 0) for (int q = nz + tid; q < ((nz + 1) & ~1); q += PACK_T) bva[q] = 0.0;
   __syncthreads();
+  const int nslot = wt > 0 ? wt * R : nz;                    // entries of bci to translate (padding included)
   int nu = nz;
   if (nz <= PACK_CAP) {
     int np2 = 1;
     while (np2 < nz) np2 <<= 1;
-    for (int q = tid; q < np2; q += PACK_T) keys[q] = q < nz ? bci[q] : 0x7fffffff;
+    // the columns of the real nonzeros (ELL padding carries 0x7fffffff and sorts to the end)
+    if (wt > 0) {
+      __shared__ int s_cnt;
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      for (int e = tid; e < nslot; e += PACK_T) if (bci[e] != 0x7fffffff) keys[atomicAdd(&s_cnt, 1)] = bci[e];
+      __syncthreads();
+      for (int q = nz + tid; q < np2; q += PACK_T) keys[q] = 0x7fffffff;
+    } else {
+      for (int q = tid; q < np2; q += PACK_T) keys[q] = q < nz ? bci[q] : 0x7fffffff;
+    }
     __syncthreads();
     for (int k = 2; k <= np2; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
@@ -161,22 +178,25 @@ __global__ void __launch_bounds__(PACK_T) pack_csr_tiles_kernel(const int *__res
     }
     __syncthreads();
     nu = s_nu;
-    for (int q = tid; q < nz; q += PACK_T) {               // column -> position in the distinct list
+    for (int q = tid; q < nslot; q += PACK_T) {            // column -> position in the distinct list (padding -> 0)
       const int c = bci[q];
       int lo = 0, hi = nu - 1;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < c) lo = mid + 1; else hi = mid; }
+      if (c == 0x7fffffff) { lo = 0; }
+      else while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < c) lo = mid + 1; else hi = mid; }
       bci[q] = lo;
     }
     for (int q = tid; q < ((nu + 3) & ~3); q += PACK_T) bul[q] = q < nu ? keys[q] : 0;
   } else {
+    // more nonzeros than the sort holds: always the CSR layout (64 * max_len <= 1.25 nz + 64 cannot hold with nz > PACK_CAP
+    // unless the rows are long and regular; such tiles do not fit a ring stage anyway)
     for (int q = tid; q < ((nz + 3) & ~3); q += PACK_T) bul[q] = q < nz ? bci[q] : 0;
     __syncthreads();
     for (int q = tid; q < nz; q += PACK_T) bci[q] = q;
   }
-  for (int q = nz + tid; q < ((nz + 3) & ~3); q += PACK_T) bci[q] = 0;
-  for (int i = tid; i < R + 4; i += PACK_T) hdr[i] = i <= R ? rpl[i] : (i == R + 1 ? nu : 0);
+  if (wt == 0) for (int q = nz + tid; q < ((nz + 3) & ~3); q += PACK_T) bci[q] = 0;
+  for (int i = tid; i < R + 4; i += PACK_T) hdr[i] = i <= R ? rpl[i] : (i == R + 1 ? nu : (i == R + 2 ? wt : 0));
   if (tid == 0) {
-    const int len = tile_blob_bytes(nz, nu);
+    const int len = tile_blob_bytes(nz, nu, wt);
     tile_len[t] = len;
     atomicMax(&max_len_nu[0], len);
     atomicMax(&max_len_nu[1], nu);
