@@ -25,6 +25,11 @@ namespace bsreg {
 
 constexpr int SWEEP_TILE_ROWS = 64;
 
+// Row r of tile column c sits at position r ^ 4 (c & 3) of the column (an involution inside aligned groups of 16 rows): the
+// FP64 mma fragments of the persistent sweep (lane = (column g, row t) of an 8 x 4 block) then fall into distinct banks,
+// and lane = row readers just see a permutation of their 32 rows.
+__host__ __device__ inline int tile_row_pos(int c, int r) { return r ^ ((c & 3) << 2); }
+
 // A tile's blob: header {rp_local[R + 1], nu, wt, 1 spare}, values, column slots, ul[nu~4] (the distinct columns).
 //   wt > 0 (rows of similar length, e.g. kNN): slot-major "ELL" layout va[wt][R], ci[wt][R] -- lane = row reads consecutive
 //          addresses, no shared-memory bank conflicts; short rows are padded with (0.0, 0)

@@ -114,7 +114,7 @@ __device__ __forceinline__ void ring_gather_tile(double *Z, const unsigned char 
 #pragma unroll
       for (int u = 0; u < GU; ++u) if (u < wt) a = fma(VA[u * R + lane + 32 * hh], Yg[cl[hh][u]], a);
       for (int u = GU; u < wt; ++u) a = fma(VA[u * R + lane + 32 * hh], Yg[CI[u * R + lane + 32 * hh]], a);
-      Z[(m + 1) * R + lane + 32 * hh] = a;
+      Z[(m + 1) * R + tile_row_pos(m + 1, lane + 32 * hh)] = a;
     }
   } else {
     int pb[R / 32], pe[R / 32];
@@ -126,7 +126,7 @@ __device__ __forceinline__ void ring_gather_tile(double *Z, const unsigned char 
     for (int hh = 0; hh < R / 32; ++hh) {
       double a = 0.0;
       for (int p = pb[hh]; p < pe[hh]; ++p) a = fma(VA[p], Yg[CI[p]], a);
-      Z[(m + 1) * R + lane + 32 * hh] = a;
+      Z[(m + 1) * R + tile_row_pos(m + 1, lane + 32 * hh)] = a;
     }
   }
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes before the stage is refilled

@@ -62,7 +62,7 @@ __global__ void pack_tiles_kernel(const double *__restrict__ X, const double *__
     const int r = (int)(idx % R);
     const size_t tc = idx / R;
     const int c = (int)(tc % (m + 1)), tile = (int)(tc / (m + 1));
-    const int row = tile * R + r;
+    const int row = tile * R + tile_row_pos(c, r);                   // position r of column c holds this row
     double v = 0.0;
     if (row < n) {
       const int src = perm ? perm[row] : row;
@@ -567,6 +567,13 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, int yg_off,
     const int blk = wid % C::NBLK, wr = wid / C::NBLK;
     const int gi = bm.gi[blk], gj = bm.gj[blk];
     const bool diag = gi == gj;
+    // offsets of this lane's row in the block's columns (row swizzle of the tile: tile_row_pos; bits 2-3 of the lane only)
+    int oa[6], ob[6];
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      oa[p] = (6 * gi + p) * R + tile_row_pos(6 * gi + p, lane);
+      ob[p] = (6 * gj + p) * R + tile_row_pos(6 * gj + p, lane);
+    }
     double acc[6][6];
 #pragma unroll
     for (int p = 0; p < 6; ++p)
@@ -580,10 +587,10 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, int yg_off,
       if (!(dbg & 2))
 #pragma unroll
       for (int rr = 0; rr < (R / 32) / WPB; ++rr) {
-        const int r = lane + 32 * (wr + WPB * rr);
+        const int r32 = 32 * (wr + WPB * rr);
         double a[6], b[6];
 #pragma unroll
-        for (int p = 0; p < 6; ++p) a[p] = Z[(6 * gi + p) * R + r];
+        for (int p = 0; p < 6; ++p) a[p] = Z[oa[p] + r32];
         if (diag) {
 #pragma unroll
           for (int p = 0; p < 6; ++p)
@@ -591,7 +598,7 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, int yg_off,
             for (int q = p; q < 6; ++q) acc[p][q] = fma(a[p], a[q], acc[p][q]);
         } else {
 #pragma unroll
-          for (int p = 0; p < 6; ++p) b[p] = Z[(6 * gj + p) * R + r];
+          for (int p = 0; p < 6; ++p) b[p] = Z[ob[p] + r32];
 #pragma unroll
           for (int p = 0; p < 6; ++p)
 #pragma unroll
