@@ -43,8 +43,6 @@ def build_library(force: bool = False, verbose: bool = False, variant: str = "")
     objdir.mkdir(exist_ok=True)
     nvcc = _nvcc()
     extra = ["-DBSREG_TRACE"] if os.environ.get("BSREG_TRACE") else []   # clock64 trace points (diagnostics)
-    if os.environ.get("BSREG_CHAINS_PER_CTA"):                            # tuning knob of the persistent kernel
-        extra.append("-DBSREG_CHAINS_PER_CTA=" + os.environ["BSREG_CHAINS_PER_CTA"])
 
     def compile_one(src: str):
         obj = objdir / (src[:-3] + ".o")
