@@ -285,9 +285,21 @@ def run_ours(args):
             tot += a.elapsed_time(b)
         return tot / reps
 
-    roof = cpu = e2e = big = None
+    roof = cpu = e2e = big = more = None
     if rank == 0 and not args.skip_big:
         big = hbm_resident_check(capi, torch, hbm_peak)
+        more = []
+        for nc in (128, 256):                     # the same sweep serves more resident chains (not the headline config)
+            with capi.Handle(yp, Xp, model=capi.MODEL_SAR, prior=capi.PRIOR_INDEPENDENT, W=Wp, ldet=capi.LDET_CHEBYSHEV,
+                             cheb_order=CHEB_ORDER, cheb_probes=8, n_chains=nc, seed=7) as hm:
+                sm_ = torch.cuda.ExternalStream(hm.stream())
+                hm.run_into(0, ITERS_PER_STEP, None, None)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(sm_); hm.run_into(0, 2 * ITERS_PER_STEP, None, None); b.record(sm_)
+                torch.cuda.synchronize()
+                more.append({"chains_per_gpu": nc, "value": nc * 2 * ITERS_PER_STEP / (a.elapsed_time(b) * 1e-3),
+                             "us_per_iteration": 1e3 * a.elapsed_time(b) / (2 * ITERS_PER_STEP)})
     if rank == 0:
         sweep_warm = time_launches(h.launch_sweep, 400, False)
         sweep_cold = time_launches(h.launch_sweep, 20, True)
@@ -296,8 +308,9 @@ def run_ours(args):
         step_ms = total_ms / args.steps                       # one launch of the persistent kernel = one step
         in_loop = bytes_sweep * ITERS_PER_STEP / (step_ms * 1e-3) / 1e9
         alone = bytes_sweep / (sweep_warm * 1e-3) / 1e9
-        roof = {"kernel": "gibbs_persistent_kernel<4>: 132 sweep CTAs (TMA-fed fused CSR SpMV + Gram reduction, one "
-                          "pass over W, y, X per Gibbs iteration) + 16 chain CTAs, one cooperative launch per step",
+        roof = {"kernel": "gibbs_persistent_kernel<4, mma>: 126 sweep CTAs (TMA-fed fused CSR SpMV + Gram reduction on the FP64 "
+                          "tensor cores, one pass over W, y, X per Gibbs iteration) + 22 chain CTAs (3 chains each), one "
+                          "cooperative launch per step",
                 "bound": "hbm", "achieved": in_loop, "peak": hbm_peak, "unit": "GB/s", "frac": in_loop / hbm_peak,
                 "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE,
                 "algorithmic_bytes": bytes_sweep * ITERS_PER_STEP,
@@ -361,7 +374,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clk,
-            "cached_stats_value": cached_value,
+            "cached_stats_value": cached_value, "more_resident_chains": more,
             "hbm_roofline_chain_iter_s": hbm_peak * 1e9 / h_bytes_per_chain_iter(bytes_sweep) * world,
         }))
     if dist is not None:
