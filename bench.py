@@ -38,7 +38,7 @@ E2E_BURN, E2E_SAVE = 500, 1000           # defaults of bm(), R/60_interface.R:39
 METRIC = "SAR Gibbs chain-iter/s at N=100k, 64 chains/GPU"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the persistent kernel (500 iterations), from the
 # `ncu --set full` capture summarised in profiles/ (None until a capture of the current kernel is committed)
-NCU_DRAM_BYTES_PER_LAUNCH = 31842048 + 0
+NCU_DRAM_BYTES_PER_LAUNCH = 31804416 + 512
 NCU_TRAFFIC_SOURCE = ("ncu dram__bytes_read.sum + dram__bytes_write.sum of one 500-iteration launch "
                       "(profiles/r1_persistent_final_dram_bytes.csv); full capture: profiles/r1_persistent_final_ncu_full.txt")
 
@@ -389,13 +389,14 @@ def hbm_resident_check(capi, torch, hbm_peak):
     with capi.Handle(p.y, p.X, model=capi.MODEL_SAR, W=p.W, ldet=capi.LDET_CHEBYSHEV, cheb_order=CHEB_ORDER,
                      cheb_probes=8, n_chains=CHAINS_PER_GPU, seed=5) as hb:
         st = torch.cuda.ExternalStream(hb.stream())
-        hb.run_into(0, 100, None, None)
+        hb.run_into(0, 400, None, None)                       # warm-up (clocks, instruction caches)
         torch.cuda.synchronize()
-        iters = 200
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(st); hb.run_into(0, iters, None, None); b.record(st)
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b)
+        iters, ms = 400, 1e30
+        for _ in range(3):                                    # best of three launches of 400 iterations
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st); hb.run_into(0, iters, None, None); b.record(st)
+            torch.cuda.synchronize()
+            ms = min(ms, a.elapsed_time(b))
         gbs = hb.sweep_bytes() * iters / (ms * 1e-3) / 1e9
         return {"workload": "synthetic SAR, N=1000000, kNN(k=10), K=20, 64 chains", "us_per_iteration": 1e3 * ms / iters,
                 "algorithmic_bytes_per_iteration": hb.sweep_bytes(), "achieved": gbs, "unit": "GB/s", "frac": gbs / hbm_peak,
