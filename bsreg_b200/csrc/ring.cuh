@@ -75,6 +75,37 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 }
 
 
+// FP64 tensor-core form of the Gram update (NG = 4, i.e. 24 tile columns = 3 groups of 8): D (8 x 8) += A (8 x 4) B (4 x 8)
+// with A[g][t] = Z[r0 + t][8 I + g], B[t][g] = Z[r0 + t][8 J + g] -- the same register serves as A fragment of column group I
+// and as B fragment of column group I, so a step of 4 rows costs 3 LDS.64 and 6 mma (the upper-triangular block pairs)
+// instead of 96 LDS.64 per row from ten warps.  Lane l holds D[l >> 2][2 (l & 3)], D[l >> 2][2 (l & 3) + 1].
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+constexpr int MMA_BLOCKS = 6, MMA_WARPS = 4;                          // block pairs (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+__host__ __device__ constexpr int mma_bi(int b) { return b < 3 ? 0 : (b < 5 ? 1 : 2); }
+__host__ __device__ constexpr int mma_bj(int b) { return b < 3 ? b : (b < 5 ? b - 2 : 2); }
+// one tile on the tensor cores: warp w of MMA_WARPS takes the 4-row steps w, w + 4, ... (row swizzle: tile_row_pos)
+__device__ __forceinline__ void mma_tile(double (&acc)[MMA_BLOCKS][2], const double *Z, const int (&fo)[3], int wid) {
+  constexpr int R = SWEEP_TILE_ROWS;
+#pragma unroll
+  for (int ks = 0; ks < R / (4 * MMA_WARPS); ++ks) {
+    const int r0 = 4 * (wid + MMA_WARPS * ks);
+    double f[3];
+#pragma unroll
+    for (int cg = 0; cg < 3; ++cg) f[cg] = Z[fo[cg] ^ r0];            // row r0 + t at position (r0 | t) ^ sw = (t ^ sw) ^ r0
+    dmma884(acc[0], f[0], f[0]); dmma884(acc[1], f[0], f[1]); dmma884(acc[2], f[0], f[2]);
+    dmma884(acc[3], f[1], f[1]); dmma884(acc[4], f[1], f[2]); dmma884(acc[5], f[2], f[2]);
+  }
+}
+// offsets of a lane's fragment element in the three column groups
+__device__ __forceinline__ void mma_frag_offsets(int (&fo)[3], int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int cg = 0; cg < 3; ++cg) fo[cg] = (8 * cg + g) * SWEEP_TILE_ROWS + (t ^ (((8 * cg + g) & 3) << 2));
+}
+
 // Wy of one staged tile, executed by one gather warp.  The tile's blob lists the DISTINCT columns its rows reference
 // (UL, ascending ids of the permuted ordering) and the nonzeros index that list (CI), so a y value several rows share is
 // fetched once: with observations in a locality-preserving order a 64-row kNN tile (640 nonzeros) has about 200 of them

@@ -470,7 +470,9 @@ __global__ void __launch_bounds__(Ring<NG>::T, 1)
 sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, int yg_off, int dbg) {
   using C = Ring<NG>;
   const BlockMap &bm = c_block_map<NG>;
-  constexpr int T = C::T, R = C::R, NC = C::NC, WPB = C::WPB, MATH = C::MATH, MATHW = C::MATHW, GATHER = C::GATHER, NRED = C::NRED;
+  constexpr bool MMA = NG == 4;                                        // 24 tile columns: Gram update on the FP64 tensor cores
+  constexpr int T = C::T, R = C::R, NC = C::NC, WPB = C::WPB, MATHW = C::MATHW, GATHER = C::GATHER;
+  constexpr int MATH = MMA ? MMA_WARPS : C::MATH, NRED = MMA ? MMA_BLOCKS * 64 : C::NRED;
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ __align__(8) uint64_t full[RING_MAX_STAGES], lag[RING_MAX_STAGES], empty[RING_MAX_STAGES];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -487,9 +489,17 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, int yg_off,
   int gidx = -1;
   double inv = 0.0;
   if (tid < NRED) {
-    const int blk = tid / 36, e = tid - blk * 36, p = e / 6, q = e - p * 6;
-    const int ca = 6 * bm.gi[blk] + p, cb = 6 * bm.gj[blk] + q;       // tile columns
-    const bool lower = bm.gi[blk] == bm.gj[blk] && q < p;
+    int ca, cb;                                                       // tile columns
+    bool lower;
+    if (MMA) {
+      const int blk = tid >> 6, p = (tid >> 3) & 7, q = tid & 7;
+      ca = 8 * mma_bi(blk) + p; cb = 8 * mma_bj(blk) + q;
+      lower = mma_bi(blk) == mma_bj(blk) && q < p;
+    } else {
+      const int blk = tid / 36, e = tid - blk * 36, p = e / 6, q = e - p * 6;
+      ca = 6 * bm.gi[blk] + p; cb = 6 * bm.gj[blk] + q;
+      lower = bm.gi[blk] == bm.gj[blk] && q < p;
+    }
     const int ncol = has_w ? m + 2 : m + 1;
     if (!lower && ca < ncol && cb < ncol) {
       const int ga = ca < m ? 2 + ca : ca - m, gb = cb < m ? 2 + cb : cb - m;   // G index: y = 0, Wy = 1, X_a = 2 + a
@@ -518,7 +528,7 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, int yg_off,
   const uint32_t z_bytes = (uint32_t)(m + 1) * R * 8u;
 
   double *red = reinterpret_cast<double *>(ring);
-  constexpr int LD = WPB * 32 + 1;
+  constexpr int LD = MMA ? MMA_WARPS + 1 : WPB * 32 + 1;
 
   if (wid >= MATHW) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(C::REG_LIGHT));
   if (wid == MATHW + GATHER) {
@@ -574,6 +584,31 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, int yg_off,
       oa[p] = (6 * gi + p) * R + tile_row_pos(6 * gi + p, lane);
       ob[p] = (6 * gj + p) * R + tile_row_pos(6 * gj + p, lane);
     }
+    if constexpr (MMA) {
+      double acc[MMA_BLOCKS][2];
+#pragma unroll
+      for (int q = 0; q < MMA_BLOCKS; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+      int fo[3];
+      mma_frag_offsets(fo, lane);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < (wid < MATH ? my_tiles : 0); ++j) {
+        mbar_wait(&lag[s], ph);
+        if (!(dbg & 2)) mma_tile(acc, stZ(s), fo, wid);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      asm volatile("bar.sync 0;\n" ::: "memory");                     // every stage has been consumed
+      if (wid < MATH) {
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int q = 0; q < MMA_BLOCKS; ++q) {
+          red[(q * 64 + g * 8 + 2 * t) * LD + wid] = acc[q][0];
+          red[(q * 64 + g * 8 + 2 * t + 1) * LD + wid] = acc[q][1];
+        }
+      }
+    } else {
     double acc[6][6];
 #pragma unroll
     for (int p = 0; p < 6; ++p)
@@ -617,13 +652,14 @@ sweep_ring_kernel(DeviceData dd, int ntiles, int S, int stage_bytes, int yg_off,
 #pragma unroll
         for (int q = 0; q < 6; ++q) red[(blk * 36 + p * 6 + q) * LD + wr * 32 + lane] = acc[p][q];
     }
+    }
   }
   __syncthreads();
   if (gidx >= 0) {
     const double *v = red + tid * LD;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;                    // fixed order
 #pragma unroll 8
-    for (int l = 0; l < WPB * 32; l += 4) { s0 += v[l]; s1 += v[l + 1]; s2 += v[l + 2]; s3 += v[l + 3]; }
+    for (int l = 0; l < LD - 1; l += 4) { s0 += v[l]; s1 += v[l + 1]; s2 += v[l + 2]; s3 += v[l + 3]; }
     const long long f = __double2ll_rn(((s0 + s1) + (s2 + s3)) * inv);
     atomicAdd(reinterpret_cast<unsigned long long *>(dd.Gfix + (size_t)dd.gcur * d * d + gidx), (unsigned long long)f);
   }

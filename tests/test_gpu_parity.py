@@ -298,3 +298,17 @@ def test_tiles_with_long_and_empty_rows(monkeypatch):
 def capi_mod():
     from bsreg_b200 import capi
     return capi
+
+
+def test_tensor_core_and_vector_gram_updates_agree(monkeypatch):
+    """The persistent sweep forms Z'Z on the FP64 tensor cores (mma.m8n8k4) for 19 <= d <= 24; the vector-FMA form of the
+    same kernel (BSREG_NO_MMA=1) must give the same chains to rounding, and both follow the oracle."""
+    p = small_problem("sar", n=6000, k=20, knn=8)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("BSREG_NO_MMA", mode)
+        with cuda_handle("sar", p, seed=77, n_chains=7, chain_offset=1) as h:
+            out[mode] = h.run(25, 35)
+    assert relnorm(out["0"], out["1"]) < 1e-9
+    ref = oracle_draws(oracle_chain("sar", p, seed=77, chain=1 + 4), 35, 25)
+    assert relnorm(out["0"][4].T, ref) < 1e-7
