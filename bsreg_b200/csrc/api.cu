@@ -328,9 +328,13 @@ int trace_moments_launch(bsreg_handle *h, Shard &s, const bsreg_problem *prob_cs
     int nxt = 1;
     for (int j = 2; j <= order; ++j) {
       double *next = job.buf[nxt];
-      launch_spmm(n, s.dd.rp, s.dd.ci, s.dd.va, cur, probes, probes, next, probes, 0, 2.0, prev, -1.0, st);
-      ++h->launches;
-      if (j >= 3) { launch_dot(job.U, next, (int64_t)len, job.scratch, job.res + j, st); h->launches += 2; }
+      if (j >= 3) {          // the dot u'T_j u rides on the product
+        launch_spmm_dot(n, s.dd.rp, s.dd.ci, s.dd.va, cur, probes, next, 2.0, prev, -1.0, job.U, job.scratch, job.res + j, st);
+        h->launches += 2;
+      } else {
+        launch_spmm(n, s.dd.rp, s.dd.ci, s.dd.va, cur, probes, probes, next, probes, 0, 2.0, prev, -1.0, st);
+        ++h->launches;
+      }
       prev = cur; cur = next; nxt = (nxt + 1) % 3;
     }
   }

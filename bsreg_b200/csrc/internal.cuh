@@ -122,6 +122,8 @@ void launch_residual_ss(const DeviceData &dd, int n_eval, const double *beta,
                         const double *lam, const double *rho, double *partial, double *out, cudaStream_t s);
 void launch_probes(double *U, int n, int n_probes, uint64_t seed, cudaStream_t s);
 void launch_dot(const double *a, const double *b, int64_t len, double *partial, double *out, cudaStream_t s);
+void launch_spmm_dot(int n, const int *rp, const int *ci, const double *va, const double *B, int m, double *out, double alpha,
+                     const double *C, double beta, const double *U, double *partial, double *dot, cudaStream_t s);
 
 // launchers (chain.cu)
 size_t chain_smem_bytes(int m, int model, int prior);

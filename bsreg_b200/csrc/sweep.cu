@@ -242,11 +242,18 @@ void launch_gram_to_double(const DeviceData &dd, double *G, cudaStream_t s) {
 // one thread per (row, column); consecutive threads read consecutive columns of a
 // gathered row, so the gather is coalesced for m >= 4.
 // ---------------------------------------------------------------------------
-__global__ void csr_spmm_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci,
-                                const double *__restrict__ va, const double *__restrict__ B, int m, int ldb,
-                                double *__restrict__ out, int ldo, int col0, double alpha,
-                                const double *__restrict__ C, double beta) {
+__global__ void combine_partials_kernel(const double *partial, int nparts, int stride, int count, double *out);
+
+// DOT: also sum_{row, c} U[row][c] * out[row][c] (the Hutchinson dot u'T_j u of the trace moments, fused so that the
+// product is not read back): per-CTA partials in fixed order, combined by combine_partials_kernel
+template <bool DOT>
+__global__ void __launch_bounds__(256) csr_spmm_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci,
+                                                       const double *__restrict__ va, const double *__restrict__ B, int m, int ldb,
+                                                       double *__restrict__ out, int ldo, int col0, double alpha,
+                                                       const double *__restrict__ C, double beta,
+                                                       const double *__restrict__ U, double *__restrict__ partial) {
   const size_t total = (size_t)n * m;
+  double dot = 0.0;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int row = (int)(idx / m), c = (int)(idx % m);
     double acc = 0.0;
@@ -254,6 +261,18 @@ __global__ void csr_spmm_kernel(int n, const int *__restrict__ rp, const int *__
     double v = alpha * acc;
     if (C != nullptr) v += beta * C[(size_t)row * ldo + col0 + c];
     out[(size_t)row * ldo + col0 + c] = v;
+    if (DOT) dot = fma(U[(size_t)row * ldo + col0 + c], v, dot);
+  }
+  if (DOT) {
+    __shared__ double red[8];
+    dot = warp_sum(dot);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      partial[blockIdx.x] = t;
+    }
   }
 }
 
@@ -262,7 +281,19 @@ void launch_spmm(int n, const int *rp, const int *ci, const double *va, const do
   const size_t total = (size_t)n * m;
   const int block = 256;
   const int grid = (int)((total + block - 1) / block < 148 * 16 ? (total + block - 1) / block : 148 * 16);
-  csr_spmm_kernel<<<grid > 0 ? grid : 1, block, 0, s>>>(n, rp, ci, va, B, m, ldb, out, ldo, col0, alpha, C, beta);
+  csr_spmm_kernel<false><<<grid > 0 ? grid : 1, block, 0, s>>>(n, rp, ci, va, B, m, ldb, out, ldo, col0, alpha, C, beta,
+                                                                nullptr, nullptr);
+}
+
+// out = alpha W B + beta C and *dot = sum(U .* out), U laid out like out; `partial` holds one double per CTA (<= 2368)
+void launch_spmm_dot(int n, const int *rp, const int *ci, const double *va, const double *B, int m, double *out, double alpha,
+                     const double *C, double beta, const double *U, double *partial, double *dot, cudaStream_t s) {
+  const size_t total = (size_t)n * m;
+  const int block = 256;
+  int grid = (int)((total + block - 1) / block < 148 * 16 ? (total + block - 1) / block : 148 * 16);
+  if (grid < 1) grid = 1;
+  csr_spmm_kernel<true><<<grid, block, 0, s>>>(n, rp, ci, va, B, m, m, out, m, 0, alpha, C, beta, U, partial);
+  combine_partials_kernel<<<1, 32, 0, s>>>(partial, grid, 1, 1, dot);
 }
 
 // ---------------------------------------------------------------------------

@@ -312,3 +312,14 @@ def test_tensor_core_and_vector_gram_updates_agree(monkeypatch):
     assert relnorm(out["0"], out["1"]) < 1e-9
     ref = oracle_draws(oracle_chain("sar", p, seed=77, chain=1 + 4), 35, 25)
     assert relnorm(out["0"][4].T, ref) < 1e-7
+
+
+@pytest.mark.parametrize("n_chains", [1, 75])
+def test_persistent_kernel_chain_counts(n_chains):
+    """One resident chain (the reference's default) and more than 72 (four chains per chain CTA instead of three)."""
+    p = small_problem("sar", n=3000, k=13, knn=7)
+    with cuda_handle("sar", p, seed=31, n_chains=n_chains) as h:
+        got = h.run(20, 25)
+    for c in sorted({0, n_chains - 1, n_chains // 2}):
+        ref = oracle_draws(oracle_chain("sar", p, seed=31, chain=c), 25, 20)
+        assert relnorm(got[c].T, ref) < 1e-7, c
