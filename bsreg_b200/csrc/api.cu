@@ -504,7 +504,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   // internal ordering of the observations for the tiled sweep (the Gram matrix does not depend on it): breadth-first when
   // W has no locality.  Host work, done here so that it runs beside the uploads and transposes enqueued above.
   std::vector<int> perm;
-  if (h->model != BSREG_MODEL_LM && d <= 24 && p->nnz > 0 && wants_reorder(n, p->row_ptr, p->col_idx))
+  if (h->model != BSREG_MODEL_LM && d <= 88 && p->nnz > 0 && wants_reorder(n, p->row_ptr, p->col_idx))
     bfs_order(n, p->row_ptr, p->col_idx, perm);
   CU(cudaStreamSynchronize(s.stream));
   pool_free(tmp);
@@ -514,6 +514,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   // ---- tile-blocked operands of the ring sweep (sweep.cu): Zt and the per-tile CSR blobs ----
   dd.Zt = nullptr; dd.csr_blob = nullptr; dd.tile_off = nullptr; dd.tile_len = nullptr; dd.yp = y;
   dd.tile_max_blob = 0; dd.tile_max_nu = 0;
+  dd.sw_rp = nullptr; dd.sw_ci = nullptr; dd.sw_va = nullptr; dd.sw_X = nullptr; dd.sw_y = nullptr;
   {
     constexpr int R = SWEEP_TILE_ROWS;
     const int ntiles = (n + R - 1) / R;
@@ -569,6 +570,23 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
         CU(cudaStreamSynchronize(s.stream));
       }
       if (permuted) { pool_free(dperm); pool_free(dinv); }
+    } else if (permuted) {
+      // designs the ring does not cover (SEM, 24 < d <= 88) sweep W, X, y directly: give them the internal ordering too
+      std::vector<int> inv(n), rpn(n + 1, 0);
+      for (int r = 0; r < n; ++r) { inv[perm[r]] = r; rpn[r + 1] = rpn[r] + (p->row_ptr[perm[r] + 1] - p->row_ptr[perm[r]]); }
+      int *dperm = nullptr, *dinv = nullptr, *srp, *sci;
+      double *sva, *sX, *sy;
+      CU(pool_malloc((void **)&dperm, (size_t)n * 4)); CU(pool_malloc((void **)&dinv, (size_t)n * 4));
+      TRY(s.alloc(&srp, (size_t)n + 1)); TRY(s.alloc(&sci, (size_t)p->nnz + 8)); TRY(s.alloc(&sva, (size_t)p->nnz + 4));
+      TRY(s.alloc(&sX, (size_t)n * m)); TRY(s.alloc(&sy, (size_t)n));
+      TRY(upload(s, perm.data(), dperm, (size_t)n * 4));
+      TRY(upload(s, inv.data(), dinv, (size_t)n * 4));
+      TRY(upload(s, rpn.data(), srp, ((size_t)n + 1) * 4));
+      launch_permute_problem(rp, ci, va, X, y, dperm, dinv, srp, sci, sva, sX, sy, n, m, s.stream);
+      h->launches += 1;
+      CU(cudaStreamSynchronize(s.stream));                   // host temporaries
+      pool_free(dperm); pool_free(dinv);
+      dd.sw_rp = srp; dd.sw_ci = sci; dd.sw_va = sva; dd.sw_X = sX; dd.sw_y = sy;
     }
   }
 

@@ -57,6 +57,10 @@ struct DeviceData {
   const double *yp;           // y in the ordering of the tiles
   int tile_max_blob;          // largest used blob of one tile (bytes)
   int tile_max_nu;            // most distinct columns in one tile
+  // W, X, y in the internal ordering for the sweeps that read them directly (sweep_gram_kernel: SEM, 24 < d <= 88);
+  // null = the caller's ordering is local enough and is used as it is
+  const int *sw_rp, *sw_ci;
+  const double *sw_va, *sw_X, *sw_y;
   double *Wy, *WX;            // cached lags (R/15_sar.R:57, R/15_sem.R:63-64): direct-form kernel, generic sweep
   long long *Gfix;            // 3 * d*d
   int gcur, gzero;            // buffer this launch accumulates into / reads; buffer a sweep clears (-1: none)
@@ -115,6 +119,9 @@ void launch_pack_tiles(const double *X, const double *y, const int *perm, double
 void launch_gram_to_double(const DeviceData &dd, double *G, cudaStream_t s);
 void launch_pack_csr_tiles(const int *rp, const int *ci, const double *va, const int *perm, const int *inv,
                            const long long *tile_off, int *tile_len, int *max_len_nu, unsigned char *blob, int n, cudaStream_t s);
+void launch_permute_problem(const int *rp, const int *ci, const double *va, const double *X, const double *y, const int *perm,
+                            const int *inv, const int *rp_new, int *ci_new, double *va_new, double *X_new, double *y_new,
+                            int n, int m, cudaStream_t s);
 void launch_trace_w2_rows(int n, const int *rp, const int *ci, const double *va, double *rowsum, cudaStream_t s);
 void launch_sweep(const DeviceData &dd, int sm_count, cudaStream_t s);
 int  sweep_launch_count();

@@ -209,6 +209,28 @@ void launch_pack_csr_tiles(const int *rp, const int *ci, const double *va, const
   pack_csr_tiles_kernel<<<ntiles, PACK_T, 0, s>>>(rp, ci, va, perm, inv, tile_off, tile_len, max_len_nu, blob, n);
 }
 
+// W, X, y in the internal ordering (row r = caller's observation perm[r], columns relabelled by inv; the entries of a row
+// keep their order): one warp per row
+__global__ void permute_problem_kernel(const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
+                                       const double *__restrict__ X, const double *__restrict__ y, const int *__restrict__ perm,
+                                       const int *__restrict__ inv, const int *__restrict__ rp_new, int *__restrict__ ci_new,
+                                       double *__restrict__ va_new, double *__restrict__ X_new, double *__restrict__ y_new,
+                                       int n, int m) {
+  const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+    const int src = perm[r], p0 = rp[src], len = rp[src + 1] - p0, q0 = rp_new[r];
+    for (int q = lane; q < len; q += 32) { ci_new[q0 + q] = inv[ci[p0 + q]]; va_new[q0 + q] = va[p0 + q]; }
+    for (int c = lane; c < m; c += 32) X_new[(size_t)r * m + c] = X[(size_t)src * m + c];
+    if (lane == 0) y_new[r] = y[src];
+  }
+}
+
+void launch_permute_problem(const int *rp, const int *ci, const double *va, const double *X, const double *y, const int *perm,
+                            const int *inv, const int *rp_new, int *ci_new, double *va_new, double *X_new, double *y_new,
+                            int n, int m, cudaStream_t s) {
+  permute_problem_kernel<<<148 * 8, 256, 0, s>>>(rp, ci, va, X, y, perm, inv, rp_new, ci_new, va_new, X_new, y_new, n, m);
+}
+
 // rowsum[i] = sum_p W_ip W_{col[p], i}: tr(W^2) = sum_i rowsum[i] (exact second Chebyshev moment)
 __global__ void trace_w2_rows_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci,
                                      const double *__restrict__ va, double *__restrict__ rowsum) {
@@ -748,7 +770,9 @@ static void launch_sweep_nb(const DeviceData &dd, int sm_count, cudaStream_t s) 
   const int ntiles = (dd.n + Cfg::R - 1) / Cfg::R;
   int grid = sm_count * occ;
   if (grid > ntiles) grid = ntiles;
-  sweep_gram_kernel<NB><<<grid, Cfg::T, 0, s>>>(dd, ntiles);
+  DeviceData dv = dd;                              // Z'Z does not depend on the order of the observations
+  if (dd.sw_rp != nullptr) { dv.rp = dd.sw_rp; dv.ci = dd.sw_ci; dv.va = dd.sw_va; dv.X = dd.sw_X; dv.y = dd.sw_y; }
+  sweep_gram_kernel<NB><<<grid, Cfg::T, 0, s>>>(dv, ntiles);
 }
 
 void launch_sweep(const DeviceData &dd, int sm_count, cudaStream_t s) {

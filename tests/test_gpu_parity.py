@@ -323,3 +323,21 @@ def test_persistent_kernel_chain_counts(n_chains):
     for c in sorted({0, n_chains - 1, n_chains // 2}):
         ref = oracle_draws(oracle_chain("sar", p, seed=31, chain=c), 25, 20)
         assert relnorm(got[c].T, ref) < 1e-7, c
+
+
+def test_sem_sweep_in_internal_ordering(monkeypatch):
+    """SEM (and wide designs) sweep W, X, y directly; without locality they get the internal ordering too.  Same Gram matrix
+    (to rounding) and same chains with the relabelling off / on, and K1 still answers in the caller's ordering."""
+    p = _scrambled("sem", 6100, 5, 7)
+    Wy, WX = core.spmm(p.W, p.y), core.spmm(p.W, p.X)
+    G_ref = core.gram(p.y, p.X, Wy, WX)
+    scale = np.sqrt(np.outer(np.diag(G_ref), np.diag(G_ref)))
+    G, draws = {}, {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("BSREG_REORDER", mode)
+        with cuda_handle("sem", p, seed=4, n_chains=3, ldet=capi_mod().LDET_CHEBYSHEV, cheb_order=12, cheb_probes=8) as h:
+            G[mode] = h.eval_gram()
+            assert relnorm(h.eval_spmm(p.X), WX) < 1e-13
+            draws[mode] = h.run(15, 20)
+        assert np.max(np.abs(G[mode] - G_ref) / scale) < 1e-13, mode
+    assert relnorm(draws["0"], draws["1"]) < 1e-9
