@@ -228,12 +228,12 @@ int build_graph(bsreg_handle *h, Shard &s) {
 
 int enqueue_iterations(bsreg_handle *h, Shard &s, int count, const RunCtl &ctl) {
   const bool streamed = h->stats_mode == BSREG_STATS_STREAM;
-  if (streamed && count >= 3 && persistent_supported(s.dd, h->pr, s.cs.n_chains, s.sm_count)) {
+  if (count >= 3 && persistent_supported(s.dd, h->pr, s.cs.n_chains, s.sm_count)) {
     // one cooperative launch for the whole block: sweep CTAs and chain CTAs meet at the triple-buffered Gram matrix
     const size_t gbytes = (size_t)3 * h->d * h->d * 8;
     CU(cudaMemsetAsync(s.dd.Gfix, 0, gbytes, s.stream));
     CU(cudaMemsetAsync(s.psync, 0, persistent_sync_bytes(), s.stream));
-    CU(launch_persistent(s.dd, h->pr, s.cs, ctl, s.draws_dev, count, s.psync, s.sm_count, s.stream));
+    CU(launch_persistent(s.dd, h->pr, s.cs, ctl, s.draws_dev, count, !streamed, s.psync, s.sm_count, s.stream));
     // the last Gram matrix is in buffer (count - 1) % 3; the other two were consumed but not recycled: clear them
     for (int k = 0; k < 2; ++k)
       CU(cudaMemsetAsync(s.dd.Gfix + (size_t)((count + k) % 3) * h->d * h->d, 0, gbytes / 3, s.stream));

@@ -150,7 +150,7 @@ void launch_chain_step(const DeviceData &dd, const Priors &pr, const ChainState 
 bool persistent_supported(const DeviceData &dd, const Priors &pr, int n_chains, int sm_count);
 size_t persistent_sync_bytes();
 cudaError_t launch_persistent(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl &ctl, double *draws,
-                              int K, void *sync, int sm_count, cudaStream_t s);
+                              int K, bool cached, void *sync, int sm_count, cudaStream_t s);
 
 void launch_eval_logdet(const DeviceData &dd, int n_eval, const double *v, double *out, cudaStream_t s);
 void launch_eval_conditionals(const DeviceData &dd, const Priors &pr, const double *mu0, int n_eval, const double *beta,

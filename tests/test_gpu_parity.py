@@ -341,3 +341,21 @@ def test_sem_sweep_in_internal_ordering(monkeypatch):
             draws[mode] = h.run(15, 20)
         assert np.max(np.abs(G[mode] - G_ref) / scale) < 1e-13, mode
     assert relnorm(draws["0"], draws["1"]) < 1e-9
+
+
+def test_persistent_kernel_with_cached_statistics():
+    """BSREG_STATS_CACHED (the reference's schedule: statistics formed once) also runs the persistent kernel -- the sweeps
+    fill the three Gram buffers once per launch -- and must follow the oracle, continuation included, and equal the
+    streamed run bit for bit (same Gram matrix in every buffer, same chain code)."""
+    from bsreg_b200 import capi
+    p = small_problem("sar", n=3000, k=20, knn=7)
+    with cuda_handle("sar", p, seed=19, n_chains=5, stats_mode=capi.STATS_CACHED) as h:
+        a = h.run(30, 20)
+        b = h.run(0, 15)
+        got = np.concatenate([a, b], axis=2)
+        assert h.get_state()["iterations"].tolist() == [65] * 5
+    ref = oracle_draws(oracle_chain("sar", p, seed=19, chain=3), 35, 30)
+    assert relnorm(got[3].T, ref) < 1e-7
+    with cuda_handle("sar", p, seed=19, n_chains=5) as h:
+        streamed = h.run(30, 35)
+    assert np.array_equal(streamed, got)
