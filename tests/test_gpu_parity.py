@@ -359,3 +359,19 @@ def test_persistent_kernel_with_cached_statistics():
     with cuda_handle("sar", p, seed=19, n_chains=5) as h:
         streamed = h.run(30, 35)
     assert np.array_equal(streamed, got)
+
+
+def test_persistent_kernel_short_and_uneven_blocks():
+    """Continuing a fit (bm.bm, R/60_interface.R:71-78) in launches of 3, 4, 5 and 7 iterations (every phase of the
+    triple-buffered Gram rotation) reproduces the uninterrupted chain bit for bit; with one- and two-iteration blocks in
+    between (they run the one-launch-per-stage kernels, compiled separately) it agrees to rounding.  (The burn-in stays in
+    one call: the tuning schedule of R/50_execute.R:62-71 counts iterations per call.)"""
+    p = small_problem("sar", n=2500, k=15, knn=6)
+    with cuda_handle("sar", p, seed=2, n_chains=4) as h:
+        whole = h.run(21, 19)
+    with cuda_handle("sar", p, seed=2, n_chains=4) as h:
+        parts = [h.run(21, 3)] + [h.run(0, k) for k in (4, 5, 7)]
+    assert np.array_equal(np.concatenate(parts, axis=2), whole)
+    with cuda_handle("sar", p, seed=2, n_chains=4) as h:
+        parts = [h.run(21, 1)] + [h.run(0, k) for k in (3, 2, 6, 7)]
+    assert relnorm(np.concatenate(parts, axis=2), whole) < 1e-9
