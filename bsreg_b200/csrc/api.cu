@@ -135,6 +135,7 @@ struct Shard {
   int save_cap = 0;
   double *p0_init = nullptr, *beta0 = nullptr;
   double *scratch = nullptr;          // partial sums for deterministic reductions
+  bool no_coop = false, coop_checked = false;   // the cooperative (persistent) launch was refused on this device
   cudaGraphExec_t graph = nullptr, sweep_graph = nullptr, chain_graph = nullptr;
 
   template <class T>
@@ -226,14 +227,43 @@ int build_graph(bsreg_handle *h, Shard &s) {
   return BSREG_OK;
 }
 
+// The cooperative launch can be refused before anything runs (then nothing must have been touched: the Gram buffers are
+// cleared only once the occupancy check has passed).
+static cudaError_t launch_persistent_checked(bsreg_handle *h, Shard &s, const RunCtl &ctl, int count, bool cached, size_t gbytes) {
+  if (!s.coop_checked) {
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s.dev);
+    s.coop_checked = true;
+    if (!coop) return cudaErrorNotSupported;
+  }
+  cudaError_t e = cudaMemsetAsync(s.dd.Gfix, 0, gbytes, s.stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s.psync, 0, persistent_sync_bytes(), s.stream);
+  if (e != cudaSuccess) return e;
+  const char *force = getenv("BSREG_FORCE_COOP_FAIL");             // test hook: behave as if the launch had been refused
+  if (force && *force == '1') e = cudaErrorCooperativeLaunchTooLarge;
+  else e = launch_persistent(s.dd, h->pr, s.cs, ctl, s.draws_dev, count, cached, s.psync, s.sm_count, s.stream);
+  if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+    // the buffers were cleared: rebuild the Gram matrix the one-launch path expects (one sweep into buffer 0)
+    cudaGetLastError();
+    s.seq = 0;
+    enqueue_sweep(h, s, s.stream);
+  }
+  return e;
+}
+
 int enqueue_iterations(bsreg_handle *h, Shard &s, int count, const RunCtl &ctl) {
   const bool streamed = h->stats_mode == BSREG_STATS_STREAM;
-  if (count >= 3 && persistent_supported(s.dd, h->pr, s.cs.n_chains, s.sm_count)) {
+  if (count >= 3 && !s.no_coop && persistent_supported(s.dd, h->pr, s.cs.n_chains, s.sm_count)) {
     // one cooperative launch for the whole block: sweep CTAs and chain CTAs meet at the triple-buffered Gram matrix
     const size_t gbytes = (size_t)3 * h->d * h->d * 8;
-    CU(cudaMemsetAsync(s.dd.Gfix, 0, gbytes, s.stream));
-    CU(cudaMemsetAsync(s.psync, 0, persistent_sync_bytes(), s.stream));
-    CU(launch_persistent(s.dd, h->pr, s.cs, ctl, s.draws_dev, count, !streamed, s.psync, s.sm_count, s.stream));
+    const cudaError_t le = launch_persistent_checked(h, s, ctl, count, !streamed, gbytes);
+    if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported || le == cudaErrorLaunchOutOfResources) {
+      // not every CTA can be resident here (MPS share, MIG slice, ...): this device keeps to one launch per stage
+      cudaGetLastError();
+      s.no_coop = true;
+      return enqueue_iterations(h, s, count, ctl);
+    }
+    CU(le);
     // the last Gram matrix is in buffer (count - 1) % 3; the other two were consumed but not recycled: clear them
     for (int k = 0; k < 2; ++k)
       CU(cudaMemsetAsync(s.dd.Gfix + (size_t)((count + k) % 3) * h->d * h->d, 0, gbytes / 3, s.stream));

@@ -375,3 +375,19 @@ def test_persistent_kernel_short_and_uneven_blocks():
     with cuda_handle("sar", p, seed=2, n_chains=4) as h:
         parts = [h.run(21, 1)] + [h.run(0, k) for k in (3, 2, 6, 7)]
     assert relnorm(np.concatenate(parts, axis=2), whole) < 1e-9
+
+
+def test_refused_cooperative_launch_falls_back_to_single_launches(monkeypatch):
+    """If the device cannot hold every CTA of the persistent kernel (MPS share, MIG slice) the cooperative launch is
+    refused before anything runs; the handle then keeps to one launch per stage -- still on the GPU, same chains."""
+    p = small_problem("sar", n=2600, k=16, knn=6)
+    with cuda_handle("sar", p, seed=6, n_chains=4) as h:
+        want = h.run(20, 20)
+    monkeypatch.setenv("BSREG_FORCE_COOP_FAIL", "1")
+    with cuda_handle("sar", p, seed=6, n_chains=4) as h:
+        got = np.concatenate([h.run(20, 8), h.run(0, 12)], axis=2)
+        G = h.eval_gram()
+    monkeypatch.delenv("BSREG_FORCE_COOP_FAIL")
+    assert relnorm(got, want) < 1e-9
+    G_ref = core.gram(p.y, p.X, core.spmm(p.W, p.y), None)
+    assert np.max(np.abs(G - G_ref)) / np.max(np.abs(G_ref)) < 1e-12
