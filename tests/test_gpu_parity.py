@@ -391,3 +391,14 @@ def test_refused_cooperative_launch_falls_back_to_single_launches(monkeypatch):
     assert relnorm(got, want) < 1e-9
     G_ref = core.gram(p.y, p.X, core.spmm(p.W, p.y), None)
     assert np.max(np.abs(G - G_ref)) / np.max(np.abs(G_ref)) < 1e-12
+
+
+def test_wide_design_sweep_in_internal_ordering(monkeypatch):
+    """24 < d <= 88 (here K = 30) also sweeps W, X, y directly: same Gram matrix with the relabelling off / on."""
+    p = _scrambled("sar", 5200, 30, 6)
+    G_ref = core.gram(p.y, p.X, core.spmm(p.W, p.y), None)
+    scale = np.sqrt(np.outer(np.diag(G_ref), np.diag(G_ref)))
+    for mode in ("0", "1"):
+        monkeypatch.setenv("BSREG_REORDER", mode)
+        with cuda_handle("sar", p, ldet=capi_mod().LDET_CHEBYSHEV, cheb_order=8, cheb_probes=4) as h:
+            assert np.max(np.abs(h.eval_gram() - G_ref) / scale) < 1e-13, mode
