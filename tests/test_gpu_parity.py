@@ -402,3 +402,19 @@ def test_wide_design_sweep_in_internal_ordering(monkeypatch):
         monkeypatch.setenv("BSREG_REORDER", mode)
         with cuda_handle("sar", p, ldet=capi_mod().LDET_CHEBYSHEV, cheb_order=8, cheb_probes=4) as h:
             assert np.max(np.abs(h.eval_gram() - G_ref) / scale) < 1e-13, mode
+
+
+def test_slot_major_tiles_wider_than_the_unrolled_gather():
+    """Rows of 13 nonzeros: the slot-major (ELL) tile layout with more slots than the gather loop unrolls (10)."""
+    p = make_problem("sar", n=4500, k_reg=9, knn=13)
+    G_ref = core.gram(p.y, p.X, core.spmm(p.W, p.y), None)
+    scale = np.sqrt(np.outer(np.diag(G_ref), np.diag(G_ref)))
+    with cuda_handle("sar", p, ldet=capi_mod().LDET_CHEBYSHEV, cheb_order=8, cheb_probes=4, n_chains=2, seed=3) as h:
+        assert np.max(np.abs(h.eval_gram() - G_ref) / scale) < 1e-13
+    p20 = make_problem("sar", n=4500, k_reg=20, knn=13)          # the same through the persistent kernel (d = 22, mma)
+    nodes = None
+    with cuda_handle("sar", p20, ldet=capi_mod().LDET_CHEBYSHEV, cheb_order=8, cheb_probes=4, n_chains=2, seed=3) as h:
+        nodes = h.nodes()
+        got = h.run(10, 12)
+    ref = oracle_draws(oracle_chain("sar", p20, seed=3, chain=1, nodes=nodes), 12, 10)
+    assert relnorm(got[1].T, ref) < 1e-7
