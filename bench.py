@@ -143,7 +143,7 @@ def run_reference(args):
     nodes = cpu_nodes(p)
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, CHAINS_PER_GPU))
-    iters = 300                           # about 2-3 s per step on every core used
+    iters = args.ref_iters                # 300: about 2-3 s per step on every core used
     for _ in range(min(args.warmup, 1)):
         cpu_throughput(p, nodes, 20, procs)
     t0 = time.perf_counter()
@@ -415,6 +415,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-big", action="store_true", help="skip the N = 1e6 HBM-resident check (saves ~25 s)")
     ap.add_argument("--skip-cpu", action="store_true", help="shrink the CPU baseline sample to 40 iterations (profiler runs)")
+    ap.add_argument("--ref-iters", type=int, default=300, help="iterations per chain and step of the reference arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
