@@ -36,11 +36,18 @@ CHEB_ORDER, CHEB_PROBES = 50, 64
 ITERS_PER_STEP = 500
 E2E_BURN, E2E_SAVE = 500, 1000           # defaults of bm(), R/60_interface.R:39
 METRIC = "SAR Gibbs chain-iter/s at N=100k, 64 chains/GPU"
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the persistent kernel (500 iterations), from the
-# `ncu --set full` capture summarised in profiles/ (None until a capture of the current kernel is committed)
-NCU_DRAM_BYTES_PER_LAUNCH = 31804416 + 512
-NCU_TRAFFIC_SOURCE = ("ncu dram__bytes_read.sum + dram__bytes_write.sum of one 500-iteration launch "
-                      "(profiles/r1_persistent_final_dram_bytes.csv); full capture: profiles/r1_persistent_final_ncu_full.txt")
+CFG5_N, CFG5_CHAINS = 1_000_000, 512      # BASELINE.json configs[4]: SEM, N = 1e6, 512 chains over 2/4/8 GPUs
+CFG5_ITERS = 200
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the persistent kernel, from the committed ncu capture
+    (profiles/ncu_traffic.json, stamped with the commit it was taken at); None when no capture is committed."""
+    try:
+        d = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        return int(d["dram_bytes_per_launch"]), d
+    except Exception:
+        return None, None
 
 
 def load_peaks():
@@ -286,20 +293,29 @@ def run_ours(args):
         return tot / reps
 
     roof = cpu = e2e = big = more = None
+    traffic, traffic_src = ncu_traffic()
+    big_p = None
+    if not args.skip_big:
+        from bsreg_b200.synthetic import make_problem, with_model
+        big_p = make_problem("sem", n=CFG5_N, k_reg=K_REG, knn=KNN)          # cfg5's data; rank 0 reuses W, X for the SAR check
     if rank == 0 and not args.skip_big:
-        big = hbm_resident_check(capi, torch, hbm_peak)
+        big = hbm_resident_check(capi, torch, hbm_peak, with_model(big_p, "sar"))
         more = []
         for nc in (128, 256):                     # the same sweep serves more resident chains (not the headline config)
             with capi.Handle(yp, Xp, model=capi.MODEL_SAR, prior=capi.PRIOR_INDEPENDENT, W=Wp, ldet=capi.LDET_CHEBYSHEV,
                              cheb_order=CHEB_ORDER, cheb_probes=8, n_chains=nc, seed=7) as hm:
                 sm_ = torch.cuda.ExternalStream(hm.stream())
-                hm.run_into(0, ITERS_PER_STEP, None, None)
+                hm.run_into(0, 2 * ITERS_PER_STEP, None, None)      # warm-up with the timed shape (draw buffer, caches)
                 torch.cuda.synchronize()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(sm_); hm.run_into(0, 2 * ITERS_PER_STEP, None, None); b.record(sm_)
-                torch.cuda.synchronize()
-                more.append({"chains_per_gpu": nc, "value": nc * 2 * ITERS_PER_STEP / (a.elapsed_time(b) * 1e-3),
-                             "us_per_iteration": 1e3 * a.elapsed_time(b) / (2 * ITERS_PER_STEP)})
+                tm = []
+                for _ in range(3):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(sm_); hm.run_into(0, 2 * ITERS_PER_STEP, None, None); b.record(sm_)
+                    torch.cuda.synchronize()
+                    tm.append(a.elapsed_time(b))
+                mt = float(np.mean(tm))
+                more.append({"chains_per_gpu": nc, "value": nc * 2 * ITERS_PER_STEP / (mt * 1e-3),
+                             "us_per_iteration": 1e3 * mt / (2 * ITERS_PER_STEP), "launches_timed": 3})
     if rank == 0:
         sweep_warm = time_launches(h.launch_sweep, 400, False)
         sweep_cold = time_launches(h.launch_sweep, 20, True)
@@ -311,8 +327,13 @@ def run_ours(args):
         roof = {"kernel": "gibbs_persistent_kernel<4, mma>: 126 sweep CTAs (TMA-fed fused CSR SpMV + Gram reduction on the FP64 "
                           "tensor cores, one pass over W, y, X per Gibbs iteration) + 22 chain CTAs (3 chains each), one "
                           "cooperative launch per step",
-                "bound": "hbm", "achieved": in_loop, "peak": hbm_peak, "unit": "GB/s", "frac": in_loop / hbm_peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE,
+                "bound": "l2/issue (operands L2-resident)", "achieved": in_loop, "peak": hbm_peak, "unit": "GB/s",
+                "frac": in_loop / hbm_peak,
+                "frac_is": "ALGORITHMIC bytes (W, y, X once per Gibbs iteration, SURVEY 8d) / launch time / measured HBM copy "
+                           "peak.  At cfg4 the 29 MB of operands stay in L2 inside a launch, so this is NOT a fraction of an "
+                           "HBM roofline (it could exceed 1): the iteration is max(sweep on the L2 -> SM path, chain step "
+                           "bound by instruction issue).  The HBM-bound evidence is hbm_bound_check (same kernel, N = 1e6)",
+                "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes": bytes_sweep * ITERS_PER_STEP,
                 "algorithmic_bytes_per_iteration": bytes_sweep, "peak_source": peak_src,
                 "launch_us": step_ms * 1e3, "iterations_per_launch": ITERS_PER_STEP,
@@ -321,7 +342,7 @@ def run_ours(args):
                         "algorithmic figure is W, y, X streamed once per Gibbs iteration (SURVEY 8d).  The sweep CTAs and "
                         "the chain CTAs are balanced (sweep-bound and chain-bound times within 15 % of each other); "
                         "hbm_resident_check runs the same kernel at N = 1e6, where the operands (292 MB) exceed L2",
-                "hbm_resident_check": big,
+                "hbm_bound_check": big,
                 "sweep_alone": {"kernel": "sweep_ring_kernel<4>, one launch per sweep on 148 SMs", "launch_us": sweep_warm * 1e3,
                                 "achieved": alone, "frac": alone / hbm_peak,
                                 "cold": {"launch_us": sweep_cold * 1e3, "achieved": bytes_sweep / (sweep_cold * 1e-3) / 1e9,
@@ -353,12 +374,20 @@ def run_ours(args):
     e2e_val = e2e_steps * (E2E_BURN + E2E_SAVE) * CHAINS_PER_GPU * world / e2e_s
     lam_mean = float(draws_host.numpy()[:, -1, :].mean())
 
+    # ---- cfg5 (BASELINE.json configs[4]): SEM, N = 1e6, 512 chains sharded over the GPUs ----
+    cfg5 = cfg5_block(capi, torch, dist, rank, world, hbm_peak, big_p, barrier) if big_p is not None else None
+
+    # everything below runs on rank 0 alone; the other ranks leave the GPUs idle and wait on a HOST barrier (an NCCL
+    # barrier would keep their SMs spinning beside the one-handle fit and the CPU sample)
+    hostg = dist.new_group(backend="gloo") if dist is not None else None
     if rank == 0:
         e2e = {"value": e2e_val, "unit": "chain-iter/s", "h2d_bytes_per_step": int(h2d_bytes),
                "d2h_bytes_per_step": int(d2h_bytes), "ms_per_fit": 1e3 * e2e_s / e2e_steps,
                "what": f"bsreg_create (H2D + setup + Chebyshev moments) + bsreg_run({E2E_BURN} burn, {E2E_SAVE} save) "
-                       "+ D2H of draws, per fit, wall clock incl. host work",
+                       "+ D2H of draws, per fit, wall clock incl. host work; one process and one handle per GPU",
                "posterior_mean_lambda": lam_mean}
+        if world > 1:
+            e2e["one_handle"] = one_handle_fit(capi, torch, world, yp, Xp, Wp, k, h2d_bytes)
         # bounded CPU sample on this box's host cores
         cores = os.cpu_count() or 1
         procs = max(1, min(cores, CHAINS_PER_GPU))
@@ -374,31 +403,103 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clk,
-            "cached_stats_value": cached_value, "more_resident_chains": more,
+            "cached_stats_value": cached_value, "more_resident_chains": more, "cfg5": cfg5,
             "hbm_roofline_chain_iter_s": hbm_peak * 1e9 / h_bytes_per_chain_iter(bytes_sweep) * world,
         }))
     if dist is not None:
-        dist.barrier()
+        dist.barrier(group=hostg)
         dist.destroy_process_group()
 
 
-def hbm_resident_check(capi, torch, hbm_peak):
+def cfg5_block(capi, torch, dist, rank, world, hbm_peak, p, barrier):
+    """This rank's share of cfg5: SEM, N = 1e6, kNN(10), K = 20; 512 chains over the GPUs at N >= 2 (256 / 128 / 64 per
+    GPU), one 8-GPU share (64 chains) at N = 1.  Streamed (W, y, X swept every iteration: Gram matrix of
+    [y | Wy | X | WX], d = 42) and cached statistics; device time of CFG5_ITERS iterations, mean of three launches of the
+    warmed-up shape, MAX over ranks."""
+    c_g = CFG5_CHAINS // world if world >= 2 else 64
+    out = {"workload": f"cfg5: synthetic SEM, N={CFG5_N}, kNN(k=10), K=20, Chebyshev log-det (order 50, 8 probes); "
+                       f"{c_g} chains per GPU" + ("" if world >= 2 else " (one GPU's share of the 8-GPU configuration)"),
+           "chains_per_gpu": c_g, "global_chains": c_g * world, "iterations_timed": CFG5_ITERS, "launches_timed": 3,
+           "timing": "CUDA events on the handle's stream, mean of 3 launches, MAX over ranks"}
+    for mode, name in ((capi.STATS_STREAM, "stream"), (capi.STATS_CACHED, "cached")):
+        with capi.Handle(p.y, p.X, model=capi.MODEL_SEM, W=p.W, ldet=capi.LDET_CHEBYSHEV, cheb_order=CHEB_ORDER,
+                         cheb_probes=8, n_chains=c_g, chain_offset=rank * c_g, seed=11, stats_mode=mode) as h:
+            st = torch.cuda.ExternalStream(h.stream())
+            h.run_into(0, CFG5_ITERS, None, None)                 # warm-up with the timed shape
+            barrier()
+            tm = []
+            for _ in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(st); h.run_into(0, CFG5_ITERS, None, None); b.record(st)
+                torch.cuda.synchronize()
+                tm.append(a.elapsed_time(b))
+            ms = float(np.mean(tm))
+            if dist is not None:
+                t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            bytes_iter = h.sweep_bytes()
+            lam = float(h.fetch_draws(0, min(CFG5_ITERS, 50))[:, -1, :].mean())
+        gbs = bytes_iter * CFG5_ITERS / (ms * 1e-3) / 1e9
+        out[name] = {"us_per_iteration": 1e3 * ms / CFG5_ITERS, "value": c_g * world * CFG5_ITERS / (ms * 1e-3),
+                     "unit": "chain-iter/s", "lambda_mean_last_launch": lam}
+        if name == "stream":
+            out[name].update({"algorithmic_bytes_per_iteration": bytes_iter, "achieved": gbs, "peak": hbm_peak,
+                              "frac": gbs / hbm_peak, "bound": "hbm (292 MB of operands per iteration exceed the 126 MB L2)"})
+        barrier()
+    return out
+
+
+def one_handle_fit(capi, torch, world, yp, Xp, Wp, k, h2d_bytes):
+    """North star: "draws are gathered to the host once at the end".  ONE process, ONE handle with devices = 0..N-1
+    (bsreg_options.devices): 64 N chains, every shard set up by its own host thread, all draws written into one pinned
+    host buffer.  Also checks that the draws of a chain id do not depend on where it ran: the last device's block equals
+    a single-device run with chain_offset = 64 (N - 1) bit for bit."""
+    nch = CHAINS_PER_GPU * world
+    draws_all = torch.empty((nch, k + 2, E2E_SAVE), dtype=torch.float64, pin_memory=True)
+
+    def fit(seed, **kw):
+        kw = dict(n_chains=nch, devices=list(range(world))) | kw
+        with capi.Handle(yp, Xp, model=capi.MODEL_SAR, prior=capi.PRIOR_INDEPENDENT, W=Wp, ldet=capi.LDET_CHEBYSHEV,
+                         cheb_order=CHEB_ORDER, cheb_probes=CHEB_PROBES, seed=seed, **kw) as hh:
+            hh.run_into(E2E_BURN, E2E_SAVE, None, draws_all.data_ptr())
+
+    fit(1)
+    fits = 3
+    t0 = time.perf_counter()
+    for s in range(fits):
+        fit(100 + s)
+    dt = time.perf_counter() - t0
+    multi = draws_all.numpy()[CHAINS_PER_GPU * (world - 1):].copy()
+    fit(100 + fits - 1, n_chains=CHAINS_PER_GPU, chain_offset=CHAINS_PER_GPU * (world - 1), devices=[0])
+    single = draws_all.numpy()[:CHAINS_PER_GPU]
+    return {"value": fits * (E2E_BURN + E2E_SAVE) * nch / dt, "unit": "chain-iter/s", "ms_per_fit": 1e3 * dt / fits,
+            "devices": world, "chains": nch, "h2d_bytes_per_step": int(h2d_bytes) * world,
+            "d2h_bytes_per_step": int(draws_all.numel() * 8),
+            "draws_invariant": bool(np.array_equal(multi, single)),
+            "what": "one process, one bsreg handle over all devices (host thread per shard at create), draws of all "
+                    "chains into one pinned host buffer"}
+
+
+def hbm_resident_check(capi, torch, hbm_peak, p):
     """The same persistent kernel at N = 1e6 (SAR, K = 20, 64 chains): 292 MB of operands per iteration do not fit the
-    126 MB L2, so every iteration streams them from HBM."""
-    p = make_cfg4(1_000_000)
+    126 MB L2, so every iteration streams them from HBM.  Mean of three launches of the warmed-up shape."""
     with capi.Handle(p.y, p.X, model=capi.MODEL_SAR, W=p.W, ldet=capi.LDET_CHEBYSHEV, cheb_order=CHEB_ORDER,
                      cheb_probes=8, n_chains=CHAINS_PER_GPU, seed=5) as hb:
         st = torch.cuda.ExternalStream(hb.stream())
         hb.run_into(0, 400, None, None)                       # warm-up (clocks, instruction caches)
         torch.cuda.synchronize()
-        iters, ms = 400, 1e30
-        for _ in range(3):                                    # best of three launches of 400 iterations
+        iters, tm = 400, []
+        for _ in range(3):                                    # mean of three launches of 400 iterations
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(st); hb.run_into(0, iters, None, None); b.record(st)
             torch.cuda.synchronize()
-            ms = min(ms, a.elapsed_time(b))
+            tm.append(a.elapsed_time(b))
+        ms = float(np.mean(tm))
         gbs = hb.sweep_bytes() * iters / (ms * 1e-3) / 1e9
-        return {"workload": "synthetic SAR, N=1000000, kNN(k=10), K=20, 64 chains", "us_per_iteration": 1e3 * ms / iters,
+        return {"workload": "synthetic SAR, N=1000000, kNN(k=10), K=20, 64 chains", "bound": "hbm",
+                "timing": "mean of 3 launches x 400 iterations, warmed up with the same shape",
+                "us_per_iteration": 1e3 * ms / iters, "us_per_iteration_min": 1e3 * min(tm) / iters,
                 "algorithmic_bytes_per_iteration": hb.sweep_bytes(), "achieved": gbs, "unit": "GB/s", "frac": gbs / hbm_peak,
                 "value": CHAINS_PER_GPU * iters / (ms * 1e-3)}
 

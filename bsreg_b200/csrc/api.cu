@@ -9,8 +9,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -115,6 +117,20 @@ void pool_free(void *p) {
   g_pool_free.push_back(b);
 }
 
+// device temporary of a set-up phase: returned to the pool when the scope ends -- on the error paths too -- after the
+// stream that used it has drained
+struct PoolTmp {
+  cudaStream_t st;
+  void *p = nullptr;
+  explicit PoolTmp(cudaStream_t s) : st(s) {}
+  PoolTmp(const PoolTmp &) = delete;
+  PoolTmp &operator=(const PoolTmp &) = delete;
+  ~PoolTmp() { release(); }
+  cudaError_t get(size_t bytes) { return pool_malloc(&p, bytes); }
+  void release() { if (p) { cudaStreamSynchronize(st); pool_free(p); p = nullptr; } }
+  template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
 constexpr int GRAPH_UNROLL = 24;      // Gibbs iterations per CUDA graph launch (multiple of the 3 Gram buffers)
 constexpr int BLOCK_ITERS = 1000;     // iterations between host syncs / progress callbacks
 constexpr size_t DRAW_BUF_BYTES = (size_t)1 << 30;
@@ -156,7 +172,7 @@ struct bsreg_handle {
   Priors pr{};
   bsreg_options opt{};
   std::vector<Shard> shards;
-  int64_t launches = 0;
+  std::atomic<int64_t> launches{0};   // shards are set up by one host thread each
   int64_t nnz = 0;
   std::vector<double> node_re, node_im, node_w;
 };
@@ -468,8 +484,14 @@ static void bfs_order(int n, const int *rp, const int *ci, std::vector<int> &per
   }
 }
 
+// the internal ordering is the same for every shard: whichever shard thread gets there first computes it
+struct SharedOrder {
+  std::once_flag once;
+  std::vector<int> perm;
+};
+
 int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_options *o, int n_chains, int chain_lo,
-                MomentsJob *moments_job) {
+                MomentsJob *moments_job, SharedOrder &order) {
   CU(cudaSetDevice(s.dev));
   CU(cudaDeviceGetAttribute(&s.sm_count, cudaDevAttrMultiProcessorCount, s.dev));   // (cudaGetDeviceProperties costs milliseconds)
   if (o->stream && h->shards.size() == 1) { s.stream = (cudaStream_t)o->stream; s.own_stream = false; }
@@ -507,37 +529,38 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
 
   pt.mark("W upload");
   // ---- y, X (column-major on the host -> row-major [n][m] in HBM) ----
-  double *y, *X, *tmp;
+  double *y, *X;
   TRY(s.alloc(&y, (size_t)n)); TRY(s.alloc(&X, (size_t)n * m));
-  CU(pool_malloc((void **)&tmp, (size_t)n * std::max(k, std::max(p->k_slx, 1)) * 8));
+  PoolTmp tmp(s.stream);
+  CU(tmp.get((size_t)n * std::max(k, std::max(p->k_slx, 1)) * 8));
   TRY(upload(s, p->y, y, (size_t)n * 8));
-  TRY(upload(s, p->X, tmp, (size_t)n * k * 8));
-  launch_transpose(tmp, X, n, k, m, 0, s.stream);
+  TRY(upload(s, p->X, tmp.as<double>(), (size_t)n * k * 8));
+  launch_transpose(tmp.as<double>(), X, n, k, m, 0, s.stream);
   if (p->k_slx > 0) {   // setup_2SLX fixed-W branch, R/12_slx.R:60-68: X <- [X, Psi_SLX %*% X_SLX]
-    double *xs_rm; int *rps = rp, *cis = ci; double *vas = va;
+    const int *rps = rp, *cis = ci; const double *vas = va;
+    PoolTmp xs_rm(s.stream), trp(s.stream), tci(s.stream), tva(s.stream);
     CU(cudaStreamSynchronize(s.stream));
-    TRY(upload(s, p->X_slx, tmp, (size_t)n * p->k_slx * 8));
-    CU(pool_malloc((void **)&xs_rm, (size_t)n * p->k_slx * 8));
-    launch_transpose(tmp, xs_rm, n, p->k_slx, p->k_slx, 0, s.stream);
+    TRY(upload(s, p->X_slx, tmp.as<double>(), (size_t)n * p->k_slx * 8));
+    CU(xs_rm.get((size_t)n * p->k_slx * 8));
+    launch_transpose(tmp.as<double>(), xs_rm.as<double>(), n, p->k_slx, p->k_slx, 0, s.stream);
     if (p->nnz_slx > 0) {
-      CU(pool_malloc((void **)&rps, ((size_t)n + 1) * 4)); CU(pool_malloc((void **)&cis, (size_t)p->nnz_slx * 4)); CU(pool_malloc((void **)&vas, (size_t)p->nnz_slx * 8));
-      TRY(upload(s, p->row_ptr_slx, rps, ((size_t)n + 1) * 4));
-      TRY(upload(s, p->col_idx_slx, cis, (size_t)p->nnz_slx * 4));
-      TRY(upload(s, p->val_slx, vas, (size_t)p->nnz_slx * 8));
+      CU(trp.get(((size_t)n + 1) * 4)); CU(tci.get((size_t)p->nnz_slx * 4)); CU(tva.get((size_t)p->nnz_slx * 8));
+      TRY(upload(s, p->row_ptr_slx, trp.p, ((size_t)n + 1) * 4));
+      TRY(upload(s, p->col_idx_slx, tci.p, (size_t)p->nnz_slx * 4));
+      TRY(upload(s, p->val_slx, tva.p, (size_t)p->nnz_slx * 8));
+      rps = trp.as<int>(); cis = tci.as<int>(); vas = tva.as<double>();
     }
-    launch_spmm(n, rps, cis, vas, xs_rm, p->k_slx, p->k_slx, X, m, k, 1.0, nullptr, 0.0, s.stream);
-    CU(cudaStreamSynchronize(s.stream));
-    pool_free(xs_rm);
-    if (p->nnz_slx > 0) { pool_free(rps); pool_free(cis); pool_free(vas); }
+    launch_spmm(n, rps, cis, vas, xs_rm.as<double>(), p->k_slx, p->k_slx, X, m, k, 1.0, nullptr, 0.0, s.stream);
     h->launches += 2;
   }
   // internal ordering of the observations for the tiled sweep (the Gram matrix does not depend on it): breadth-first when
   // W has no locality.  Host work, done here so that it runs beside the uploads and transposes enqueued above.
-  std::vector<int> perm;
-  if (h->model != BSREG_MODEL_LM && d <= 88 && p->nnz > 0 && wants_reorder(n, p->row_ptr, p->col_idx))
-    bfs_order(n, p->row_ptr, p->col_idx, perm);
-  CU(cudaStreamSynchronize(s.stream));
-  pool_free(tmp);
+  std::call_once(order.once, [&] {
+    if (h->model != BSREG_MODEL_LM && d <= 88 && p->nnz > 0 && wants_reorder(n, p->row_ptr, p->col_idx))
+      bfs_order(n, p->row_ptr, p->col_idx, order.perm);
+  });
+  const std::vector<int> &perm = order.perm;
+  tmp.release();                                             // drains the stream first
   dd.y = y; dd.X = X;
   h->launches += 1;
   pt.mark("y, X upload + transpose");
@@ -570,10 +593,12 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
     if (sweep_ring_supported(d, h->model, cap_blob, cap_nu)) {
       double *zt, *yp = nullptr;
       int *dperm = nullptr, *dinv = nullptr;
+      PoolTmp tperm(s.stream), tinv(s.stream);
       if (permuted) {
         std::vector<int> inv(n);
         for (int r = 0; r < n; ++r) inv[perm[r]] = r;
-        CU(pool_malloc((void **)&dperm, (size_t)n * 4)); CU(pool_malloc((void **)&dinv, (size_t)n * 4));
+        CU(tperm.get((size_t)n * 4)); CU(tinv.get((size_t)n * 4));
+        dperm = tperm.as<int>(); dinv = tinv.as<int>();
         TRY(upload(s, perm.data(), dperm, (size_t)n * 4));
         TRY(upload(s, inv.data(), dinv, (size_t)n * 4));
         CU(cudaStreamSynchronize(s.stream));                 // `inv` is a host temporary
@@ -599,14 +624,15 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
       } else {
         CU(cudaStreamSynchronize(s.stream));
       }
-      if (permuted) { pool_free(dperm); pool_free(dinv); }
     } else if (permuted) {
       // designs the ring does not cover (SEM, 24 < d <= 88) sweep W, X, y directly: give them the internal ordering too
       std::vector<int> inv(n), rpn(n + 1, 0);
       for (int r = 0; r < n; ++r) { inv[perm[r]] = r; rpn[r + 1] = rpn[r] + (p->row_ptr[perm[r] + 1] - p->row_ptr[perm[r]]); }
       int *dperm = nullptr, *dinv = nullptr, *srp, *sci;
       double *sva, *sX, *sy;
-      CU(pool_malloc((void **)&dperm, (size_t)n * 4)); CU(pool_malloc((void **)&dinv, (size_t)n * 4));
+      PoolTmp tperm(s.stream), tinv(s.stream);
+      CU(tperm.get((size_t)n * 4)); CU(tinv.get((size_t)n * 4));
+      dperm = tperm.as<int>(); dinv = tinv.as<int>();
       TRY(s.alloc(&srp, (size_t)n + 1)); TRY(s.alloc(&sci, (size_t)p->nnz + 8)); TRY(s.alloc(&sva, (size_t)p->nnz + 4));
       TRY(s.alloc(&sX, (size_t)n * m)); TRY(s.alloc(&sy, (size_t)n));
       TRY(upload(s, perm.data(), dperm, (size_t)n * 4));
@@ -615,7 +641,6 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
       launch_permute_problem(rp, ci, va, X, y, dperm, dinv, srp, sci, sva, sX, sy, n, m, s.stream);
       h->launches += 1;
       CU(cudaStreamSynchronize(s.stream));                   // host temporaries
-      pool_free(dperm); pool_free(dinv);
       dd.sw_rp = srp; dd.sw_ci = sci; dd.sw_va = sva; dd.sw_X = sX; dd.sw_y = sy;
     }
   }
@@ -697,6 +722,9 @@ int init_chains(bsreg_handle *h, bool refresh_only) {
     launch_chain_init(s.dd, h->pr, s.cs, ci, s.stream);
     ++h->launches;
     CU(cudaGetLastError());
+  }
+  for (Shard &s : h->shards) {
+    CU(cudaSetDevice(s.dev));
     CU(cudaStreamSynchronize(s.stream));
   }
   return BSREG_OK;
@@ -720,8 +748,26 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
     return fail(BSREG_EINVAL, "Please provide a connectivity matrix (CSR row_ptr/col_idx/val)");   // R/15_sar.R:52
   if (need_w) {
     if (p->row_ptr[0] != 0 || p->row_ptr[p->n] != p->nnz) return fail(BSREG_EINVAL, "CSR row_ptr inconsistent with nnz");
-    for (int64_t q = 0; q < p->nnz; ++q)
-      if (p->col_idx[q] < 0 || p->col_idx[q] >= p->n) return fail(BSREG_EINVAL, "CSR column index out of range");
+    // one pass: index range, and max_i sum_j |W_ij| for the Chebyshev log-determinant below
+    double row_norm = 0.0;
+    for (int i = 0; i < p->n; ++i) {
+      double rs = 0.0;
+      for (int64_t q = p->row_ptr[i]; q < p->row_ptr[i + 1]; ++q) {
+        if (p->col_idx[q] < 0 || p->col_idx[q] >= p->n) return fail(BSREG_EINVAL, "CSR column index out of range");
+        rs += std::fabs(p->val[q]);
+      }
+      row_norm = std::max(row_norm, rs);
+    }
+    if (o->model != BSREG_MODEL_LM && o->ldet == BSREG_LDET_CHEBYSHEV && row_norm > 1.0 + 1e-8) {
+      // T_j(W) is bounded only if the spectrum of W lies in [-1, 1]; min(||W||_inf, ||W||_1) bounds the spectral radius.
+      // (The reference's eigenvalue method, R/15_sar.R:91-96, has no such condition: pass BSREG_LDET_NODES instead.)
+      std::vector<double> cs((size_t)p->n, 0.0);
+      for (int64_t q = 0; q < p->nnz; ++q) cs[p->col_idx[q]] += std::fabs(p->val[q]);
+      const double col_norm = *std::max_element(cs.begin(), cs.end());
+      if (col_norm > 1.0 + 1e-8)
+        return fail(BSREG_EINVAL, "BSREG_LDET_CHEBYSHEV needs the spectrum of W inside [-1, 1], but ||W||_inf = %g and "
+                                  "||W||_1 = %g: normalise W (e.g. row-standardise) or pass eigenvalue nodes", row_norm, col_norm);
+    }
   }
   if (p->k_slx > 0 && !p->X_slx) return fail(BSREG_EINVAL, "k_slx > 0 needs X_slx");
   PhaseTimer pt0;
@@ -765,14 +811,35 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
   h->shards.resize(ndev);
   int rc = BSREG_OK, lo = 0;
   MomentsJob mjob;
+  SharedOrder order;
   const bool want_moments = h->spatial && o->ldet != BSREG_LDET_NODES;
+  std::vector<int> cnts(ndev), los(ndev);
   for (int g = 0; g < ndev && rc == BSREG_OK; ++g) {
     Shard &s = h->shards[g];
     s.dev = o->n_devices > 0 && o->devices ? o->devices[g] : cur;
     if (s.dev < 0 || s.dev >= ndev_avail) { rc = fail(BSREG_EINVAL, "device %d not available", s.dev); break; }
-    const int cnt = o->n_chains / ndev + (g < o->n_chains % ndev ? 1 : 0);   // contiguous blocks of chain ids
-    rc = setup_shard(h, s, p, o, cnt, lo, g == 0 && want_moments ? &mjob : nullptr);
-    lo += cnt;
+    cnts[g] = o->n_chains / ndev + (g < o->n_chains % ndev ? 1 : 0);         // contiguous blocks of chain ids
+    los[g] = lo;
+    lo += cnts[g];
+  }
+  if (rc == BSREG_OK) {
+    if (ndev == 1) {
+      rc = setup_shard(h, h->shards[0], p, o, cnts[0], 0, want_moments ? &mjob : nullptr, order);
+    } else {
+      // one host thread per device: uploads, packing and the first sweep of all shards run side by side (the current
+      // device and the error string are per thread; the first failure is reported)
+      std::vector<int> rcs(ndev, BSREG_OK);
+      std::vector<std::string> errs(ndev);
+      std::vector<std::thread> workers;
+      for (int g = 0; g < ndev; ++g)
+        workers.emplace_back([&, g] {
+          rcs[g] = setup_shard(h, h->shards[g], p, o, cnts[g], los[g], g == 0 && want_moments ? &mjob : nullptr, order);
+          if (rcs[g] != BSREG_OK) errs[g] = g_err;
+        });
+      for (std::thread &t : workers) t.join();
+      for (int g = 0; g < ndev && rc == BSREG_OK; ++g)
+        if (rcs[g] != BSREG_OK) { rc = rcs[g]; g_err = errs[g]; }
+    }
   }
   pt.mark("shards total");
   // ---- log-determinant nodes ----
@@ -1174,7 +1241,7 @@ int64_t bsreg_sweep_bytes(const bsreg_handle *h) {
   return w + 8 * (int64_t)h->n * (h->m + 1);
 }
 
-int64_t bsreg_kernel_launches(const bsreg_handle *h) { return h ? h->launches : 0; }
+int64_t bsreg_kernel_launches(const bsreg_handle *h) { return h ? h->launches.load() : 0; }
 
 void bsreg_release_cache(void) {
   std::vector<FreeBlock> drop;

@@ -550,11 +550,7 @@ template <int NT>
 static void launch_chain_nt(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl *ctl, double *draws,
                             int mode, const InitArgs &ia, cudaStream_t s) {
   const size_t smem = chain_smem_bytes(dd.m, dd.model, pr.prior);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(chain_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  if (smem_optin((const void *)chain_kernel<NT>, smem) != cudaSuccess) return;   // the error stays pending for cudaGetLastError
   chain_kernel<NT><<<cs.n_chains, NT, smem, s>>>(dd, pr, cs, ctl, draws, mode, ia);
 }
 
@@ -645,10 +641,10 @@ void launch_eval_conditionals(const DeviceData &dd, const Priors &pr, const doub
                               double *rate1, double *rss, double *logpost, cudaStream_t s) {
   const size_t smem = chain_smem_bytes(dd.m, dd.model, pr.prior);
   if (chain_threads(dd.m) == 32) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(eval_cond_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem_optin((const void *)eval_cond_kernel<32>, smem) != cudaSuccess) return;
     eval_cond_kernel<32><<<n_eval, 32, smem, s>>>(dd, pr, mu0, beta, sigma2, lam, p0, v, mu1, rate1, rss, logpost);
   } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(eval_cond_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem_optin((const void *)eval_cond_kernel<128>, smem) != cudaSuccess) return;
     eval_cond_kernel<128><<<n_eval, 128, smem, s>>>(dd, pr, mu0, beta, sigma2, lam, p0, v, mu1, rate1, rss, logpost);
   }
 }

@@ -108,6 +108,10 @@ struct RunCtl {        // lives in device memory; updated by the host between bl
 constexpr int AUX_EXTRA = 4;
 __host__ __device__ inline int aux_len(int m) { return 2 * m + AUX_EXTRA; }
 
+// opt-in to more than 48 KB of dynamic shared memory.  cudaFuncSetAttribute is per device (context), so the largest size
+// configured so far is tracked per (device, kernel); thread-safe (one host thread per device sets shards up concurrently)
+cudaError_t smem_optin(const void *kernel, size_t bytes);
+
 // launchers (sweep.cu)
 void launch_transpose(const double *src_colmajor, double *dst_rowmajor, int n, int m, int ld_dst, int col0, cudaStream_t s);
 void launch_spmm(int n, const int *rp, const int *ci, const double *va, const double *B, int m, int ldb,

@@ -14,12 +14,32 @@
 // fixed-point integer atomics across CTAs (integer addition is associative, so the
 // result does not depend on CTA arrival order).
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "internal.cuh"
 #include "ring.cuh"
 #include "rng.cuh"
 
 namespace bsreg {
+
+cudaError_t smem_optin(const void *kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void *>, size_t> configured;
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t &have = configured[{dev, kernel}];
+  if (bytes > have) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    have = bytes;
+  }
+  return cudaSuccess;
+}
 
 static int g_sweep_launches = 0;
 int sweep_launch_count() { return g_sweep_launches; }
@@ -747,11 +767,7 @@ static void launch_sweep_ring(const DeviceData &dd, int sm_count, cudaStream_t s
   const int S = ring_stages(dd.d, dd.tile_max_blob, dd.tile_max_nu), sb = sweep_ring_stage_bytes(dd.d, dd.tile_max_blob, dd.tile_max_nu);
   size_t smem = (size_t)S * sb;
   if (smem < C::RED_BYTES) smem = C::RED_BYTES;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(sweep_ring_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  if (smem_optin((const void *)sweep_ring_kernel<NG>, smem) != cudaSuccess) return;   // the error stays pending for cudaGetLastError
   const int ntiles = (dd.n + C::R - 1) / C::R;
   const int grid = ntiles < sm_count ? ntiles : sm_count;
   static const int dbg = getenv("BSREG_DBG") ? atoi(getenv("BSREG_DBG")) : 0;   // ablation switches (profiling only)

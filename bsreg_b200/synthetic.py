@@ -87,3 +87,17 @@ def make_problem(model: str = "sar", n: int = 100_000, k_reg: int = 20, knn: int
     else:
         y = X @ beta + eps
     return Problem(y, X, W, beta, sigma, lam, model, pts)
+
+
+def with_model(p: Problem, model: str) -> Problem:
+    """The same W, X, beta and innovations as `p`, with y regenerated for another model (the kNN graph of a large
+    problem is the expensive part of make_problem)."""
+    n = len(p.y)
+    eps = p.sigma * np.random.default_rng(1004).standard_normal(n)
+    if model in ("sar", "sdm"):
+        y = neumann_solve(p.W, p.X @ p.beta + eps, p.lam)
+    elif model in ("sem", "sdem"):
+        y = p.X @ p.beta + neumann_solve(p.W, eps, p.lam)
+    else:
+        y = p.X @ p.beta + eps
+    return Problem(y, p.X, p.W, p.beta, p.sigma, p.lam, model, p.coords)

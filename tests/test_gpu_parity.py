@@ -418,3 +418,84 @@ def test_slot_major_tiles_wider_than_the_unrolled_gather():
         got = h.run(10, 12)
     ref = oracle_draws(oracle_chain("sar", p20, seed=3, chain=1, nodes=nodes), 12, 10)
     assert relnorm(got[1].T, ref) < 1e-7
+
+
+# ---------------------------------------------------------------------------
+# one process driving several devices (bsreg_options.devices): shards are set up by one host thread each
+# ---------------------------------------------------------------------------
+def _n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("devices", [[0, 0], [0, 1], [0, 1, 2, 3]])
+def test_one_handle_over_several_devices(devices):
+    """Chains are split in contiguous blocks over the listed devices (the same device twice exercises the multi-shard
+    host code on a single-GPU box); a chain id must give the same draws wherever it runs.  Each shard here holds as many
+    chains as the single-device comparison run, so the two execute the same kernels on the same grid: bit for bit."""
+    if max(devices) >= _n_devices():
+        pytest.skip(f"needs {max(devices) + 1} CUDA devices")
+    capi = capi_mod()
+    p = small_problem("sar", n=5000, k=20, knn=8)               # d = 22: persistent kernel, > 48 KB of dynamic shared memory
+    per, nd = 5, len(devices)
+    kw = dict(model=capi.MODEL_SAR, W=p.W, ldet=capi.LDET_CHEBYSHEV, cheb_order=16, cheb_probes=8, seed=41)
+    with capi.Handle(p.y, p.X, n_chains=per * nd, chain_offset=7, devices=devices, **kw) as h:
+        G = h.eval_gram()
+        a = h.run(30, 20)
+        b = h.run(0, 10)                                       # continuation on every shard
+        st = h.get_state()
+    assert st["iterations"].tolist() == [60] * (per * nd)
+    multi = np.concatenate([a, b], axis=2)
+    for g in range(nd):
+        with capi.Handle(p.y, p.X, n_chains=per, chain_offset=7 + per * g, devices=[devices[g]], **kw) as h1:
+            single = h1.run(30, 30)
+            assert np.array_equal(G, h1.eval_gram())
+        assert np.array_equal(multi[per * g:per * (g + 1)], single), g
+    # ... and a SEM design (one launch per stage, CUDA graphs per shard)
+    q = small_problem("sem", n=1500, k=4)
+    kw = dict(model=capi.MODEL_SEM, W=q.W, ldet=capi.LDET_CHEBYSHEV, cheb_order=12, cheb_probes=8, seed=5)
+    with capi.Handle(q.y, q.X, n_chains=2 * nd, devices=devices, **kw) as h:
+        multi = h.run(30, 30)
+    with capi.Handle(q.y, q.X, n_chains=2, chain_offset=2 * (nd - 1), devices=[devices[-1]], **kw) as h1:
+        assert np.array_equal(multi[2 * (nd - 1):], h1.run(30, 30))
+
+
+def test_chebyshev_rejects_unnormalised_w():
+    """T_j(W) explodes unless the spectrum of W lies in [-1, 1]: a binary contiguity matrix must be refused (the
+    reference's eigenvalue method has no such condition; eigenvalue nodes still work)."""
+    capi = capi_mod()
+    p = small_problem("sar", n=600, k=3)
+    Wb = p.W.copy()
+    Wb.data[:] = 1.0
+    with pytest.raises(capi.BsregError, match="spectrum of W"):
+        capi.Handle(p.y, p.X, model=capi.MODEL_SAR, W=Wb, ldet=capi.LDET_CHEBYSHEV)
+    # column-stochastic W (||W||_1 = 1, rows do not sum to one) is fine
+    Wc = sp_csr(p.W.T)
+    with capi.Handle(p.y, p.X, model=capi.MODEL_SAR, W=Wc, ldet=capi.LDET_CHEBYSHEV, cheb_order=8, cheb_probes=4) as h:
+        assert np.all(np.isfinite(h.eval_logdet(np.array([0.3]))))
+
+
+def sp_csr(W):
+    import scipy.sparse as sp
+    W = sp.csr_matrix(W)
+    W.sort_indices()
+    W.indices = W.indices.astype(np.int32)
+    W.indptr = W.indptr.astype(np.int32)
+    return W
+
+
+def test_chebyshev_against_exact_logdet_asymmetric():
+    """Approximation error of the Chebyshev / Hutchinson log-determinant against the exact one on a small ASYMMETRIC W
+    (kNN, complex spectrum inside the unit disc) across the lambda range: reported separately from same-input parity."""
+    capi = capi_mod()
+    p = small_problem("sar", n=1500, k=3, knn=8, symmetric=False)
+    with capi.Handle(p.y, p.X, model=capi.MODEL_SAR, W=p.W, ldet=capi.LDET_CHEBYSHEV, cheb_order=50, cheb_probes=64,
+                     seed=3) as h:
+        v = np.array([-0.9, -0.5, 0.0, 0.3, 0.6, 0.8, 0.9])
+        got = h.eval_logdet(v)
+    exact = np.array([core.ldet_dense(t, p.W) for t in v])
+    err = np.abs(got - exact)
+    assert err[2] < 1e-9                                        # log|I| = 0
+    assert np.all(err[np.abs(v) <= 0.6] < 0.15)                 # probe noise ~ sqrt(2 / (N R)) per moment
+    assert np.all(err < 1.0)                                    # measured ~0.25 at |v| = 0.9 (ADVICE r1): small beside
+    #                                                             the (N - M)/2 log rss term the MH ratio adds it to
