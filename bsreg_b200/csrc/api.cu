@@ -565,7 +565,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   h->launches += 1;
   pt.mark("y, X upload + transpose");
   // ---- tile-blocked operands of the ring sweep (sweep.cu): Zt and the per-tile CSR blobs ----
-  dd.Zt = nullptr; dd.csr_blob = nullptr; dd.tile_off = nullptr; dd.tile_len = nullptr; dd.yp = y;
+  dd.Zt = nullptr; dd.Xr = nullptr; dd.tile_ul = nullptr; dd.csr_blob = nullptr; dd.tile_off = nullptr; dd.tile_len = nullptr; dd.yp = y;
   dd.tile_max_blob = 0; dd.tile_max_nu = 0;
   dd.sw_rp = nullptr; dd.sw_ci = nullptr; dd.sw_va = nullptr; dd.sw_X = nullptr; dd.sw_y = nullptr;
   {
@@ -590,7 +590,56 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
         cap_nu = std::max(cap_nu, nz);
       }
     }
-    if (sweep_ring_supported(d, h->model, cap_blob, cap_nu)) {
+    // SEM (d = 2M + 2 <= 46): ring sweep of semsweep.cu.  Whether a tile fits a stage depends on how many FOREIGN rows
+    // it references, known only after packing: pack first, keep the result if the geometry fits.
+    bool sem_ring = false;
+    const char *nsr = getenv("BSREG_NO_SEM_RING");                                 // A/B switch (read per create)
+    const bool no_sem_ring = nsr != nullptr && *nsr != 0 && *nsr != '0';
+    if (h->model == BSREG_MODEL_SEM && m <= 22 && with_w && !no_sem_ring) {
+      const int ldx = sem_ring_ldx(m);
+      const size_t nrows = (size_t)ntiles * R;
+      PoolTmp tperm(s.stream), tinv(s.stream), txr(s.stream), typ(s.stream), tdb(s.stream), tdoff(s.stream), tdlen(s.stream);
+      int *dperm = nullptr, *dinv = nullptr;
+      if (permuted) {
+        std::vector<int> inv(n);
+        for (int r = 0; r < n; ++r) inv[perm[r]] = r;
+        CU(tperm.get((size_t)n * 4)); CU(tinv.get((size_t)n * 4));
+        dperm = tperm.as<int>(); dinv = tinv.as<int>();
+        TRY(upload(s, perm.data(), dperm, (size_t)n * 4));
+        TRY(upload(s, inv.data(), dinv, (size_t)n * 4));
+        CU(cudaStreamSynchronize(s.stream));                 // `inv` is a host temporary
+      }
+      CU(txr.get(nrows * ldx * 8)); CU(typ.get(nrows * 8));
+      CU(tdb.get((size_t)off[ntiles] + 16)); CU(tdoff.get(((size_t)ntiles + 1) * 8)); CU(tdlen.get(((size_t)ntiles + 2) * 4));
+      launch_pack_rows(X, y, dperm, txr.as<double>(), typ.as<double>(), n, m, ldx, s.stream);
+      int *dmax = tdlen.as<int>() + ntiles;
+      CU(cudaMemsetAsync(dmax, 0, 8, s.stream));
+      TRY(upload(s, off.data(), tdoff.p, ((size_t)ntiles + 1) * 8));
+      launch_pack_csr_tiles(rp, ci, va, dperm, dinv, tdoff.as<long long>(), tdlen.as<int>(), dmax, tdb.as<unsigned char>(), n,
+                            true, s.stream);
+      h->launches += 2;
+      int mx[2] = {0, 0};
+      CU(cudaMemcpyAsync(mx, dmax, 8, cudaMemcpyDeviceToHost, s.stream));
+      CU(cudaStreamSynchronize(s.stream));
+      // the lists of foreign rows leave the blobs for a ring of their own (fixed-size records)
+      PoolTmp tul(s.stream);
+      const int u_ints = sem_ul_ints(mx[1]);
+      CU(tul.get((size_t)ntiles * u_ints * 4));
+      CU(cudaMemsetAsync(dmax, 0, 4, s.stream));
+      launch_extract_ul(tdb.as<unsigned char>(), tdoff.as<long long>(), tdlen.as<int>(), dmax, tul.as<int>(), u_ints, n, s.stream);
+      ++h->launches;
+      CU(cudaMemcpyAsync(mx, dmax, 4, cudaMemcpyDeviceToHost, s.stream));
+      CU(cudaStreamSynchronize(s.stream));
+      if (sem_ring_supported(n, m, mx[0], mx[1])) {
+        sem_ring = true;
+        dd.Xr = txr.as<double>(); dd.yp = typ.as<double>(); dd.tile_ul = tul.as<int>();
+        dd.csr_blob = tdb.as<unsigned char>(); dd.tile_off = tdoff.as<long long>(); dd.tile_len = tdlen.as<int>();
+        dd.tile_max_blob = mx[0]; dd.tile_max_nu = mx[1];
+        for (PoolTmp *t : {&txr, &typ, &tdb, &tdoff, &tdlen, &tul}) { s.allocs.push_back(t->p); t->p = nullptr; }   // the shard keeps them
+      }
+    }
+    if (sem_ring) {
+    } else if (sweep_ring_supported(d, h->model, cap_blob, cap_nu)) {
       double *zt, *yp = nullptr;
       int *dperm = nullptr, *dinv = nullptr;
       PoolTmp tperm(s.stream), tinv(s.stream);
@@ -615,7 +664,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
         dmax = dlen + ntiles;
         CU(cudaMemsetAsync(dmax, 0, 8, s.stream));
         TRY(upload(s, off.data(), doff, ((size_t)ntiles + 1) * 8));
-        launch_pack_csr_tiles(rp, ci, va, dperm, dinv, doff, dlen, dmax, db, n, s.stream);
+        launch_pack_csr_tiles(rp, ci, va, dperm, dinv, doff, dlen, dmax, db, n, false, s.stream);
         h->launches += 1;
         int mx[2] = {0, 0};
         CU(cudaMemcpyAsync(mx, dmax, 8, cudaMemcpyDeviceToHost, s.stream));

@@ -55,6 +55,8 @@ struct DeviceData {
   const long long *tile_off;  // ntiles + 1 byte offsets into csr_blob (capacity of each tile)
   const int *tile_len;        // ntiles: bytes of each tile's blob actually used (what the ring copies)
   const double *yp;           // y in the ordering of the tiles
+  const int *tile_ul;         // SEM ring sweep: [ntiles][u_ints] foreign rows of every tile, last int = their number
+  const double *Xr;           // SEM ring sweep (semsweep.cu): X row-major [ntiles * R][ldx] in the ordering of the tiles (null: not used)
   int tile_max_blob;          // largest used blob of one tile (bytes)
   int tile_max_nu;            // most distinct columns in one tile
   // W, X, y in the internal ordering for the sweeps that read them directly (sweep_gram_kernel: SEM, 24 < d <= 88);
@@ -122,7 +124,17 @@ bool sweep_ring_supported(int d, int model, int max_blob, int max_nu);   // does
 void launch_pack_tiles(const double *X, const double *y, const int *perm, double *Zt, double *yp, int n, int m, cudaStream_t s);
 void launch_gram_to_double(const DeviceData &dd, double *G, cudaStream_t s);
 void launch_pack_csr_tiles(const int *rp, const int *ci, const double *va, const int *perm, const int *inv,
-                           const long long *tile_off, int *tile_len, int *max_len_nu, unsigned char *blob, int n, cudaStream_t s);
+                           const long long *tile_off, int *tile_len, int *max_len_nu, unsigned char *blob, int n,
+                           bool split_local, cudaStream_t s);
+// launchers (semsweep.cu)
+int  sem_ring_ldx(int m);
+bool sem_ring_supported(int n, int m, int max_blob, int max_nuf);
+void launch_pack_rows(const double *X, const double *y, const int *perm, double *Xr, double *yp, int n, int m, int ldx,
+                      cudaStream_t s);
+void launch_sweep_sem(const DeviceData &dd, int sm_count, cudaStream_t s);
+int  sem_ul_ints(int max_nuf);
+void launch_extract_ul(const unsigned char *blob, const long long *tile_off, int *tile_len, int *max_len, int *ul, int u_ints,
+                       int n, cudaStream_t s);
 void launch_permute_problem(const int *rp, const int *ci, const double *va, const double *X, const double *y, const int *perm,
                             const int *inv, const int *rp_new, int *ci_new, double *va_new, double *X_new, double *y_new,
                             int n, int m, cudaStream_t s);

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(PACK_T) pack_csr_tiles_kernel(const int *__res
                                                                 const double *__restrict__ va, const int *__restrict__ perm,
                                                                 const int *__restrict__ inv, const long long *__restrict__ tile_off,
                                                                 int *__restrict__ tile_len, int *__restrict__ max_len_nu,
-                                                                unsigned char *__restrict__ blob, int n) {
+                                                                unsigned char *__restrict__ blob, int n, int split_local) {
   constexpr int R = SWEEP_TILE_ROWS;
   __shared__ int rpl[R + 1], src0[R];
   __shared__ int keys[PACK_CAP];
@@ -198,20 +198,39 @@ __global__ void __launch_bounds__(PACK_T) pack_csr_tiles_kernel(const int *__res
     }
     __syncthreads();
     nu = s_nu;
+    // split_local (SEM ring sweep): the tile's own rows [r0, r0 + R) are addressed directly (index = row in the tile), the
+    // foreign columns follow as R + position in the list of foreign columns; they form a contiguous run of the sorted keys
+    int lo_own = 0, n_own = 0;
+    if (split_local) {
+      int lo = 0, hi = nu;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < r0) lo = mid + 1; else hi = mid; }
+      lo_own = lo; hi = nu;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < r0 + R) lo = mid + 1; else hi = mid; }
+      n_own = lo - lo_own;
+    }
     for (int q = tid; q < nslot; q += PACK_T) {            // column -> position in the distinct list (padding -> 0)
       const int c = bci[q];
       int lo = 0, hi = nu - 1;
       if (c == 0x7fffffff) { lo = 0; }
-      else while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < c) lo = mid + 1; else hi = mid; }
+      else {
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < c) lo = mid + 1; else hi = mid; }
+        if (split_local) lo = (c >= r0 && c < r0 + R) ? c - r0 : R + (lo < lo_own ? lo : lo - n_own);
+      }
       bci[q] = lo;
     }
-    for (int q = tid; q < ((nu + 3) & ~3); q += PACK_T) bul[q] = q < nu ? keys[q] : 0;
+    __syncthreads();
+    if (split_local) {
+      nu -= n_own;
+      for (int q = tid; q < ((nu + 3) & ~3); q += PACK_T) bul[q] = q < nu ? keys[q < lo_own ? q : q + n_own] : 0;
+    } else {
+      for (int q = tid; q < ((nu + 3) & ~3); q += PACK_T) bul[q] = q < nu ? keys[q] : 0;
+    }
   } else {
     // more nonzeros than the sort holds: always the CSR layout (64 * max_len <= 1.25 nz + 64 cannot hold with nz > PACK_CAP
     // unless the rows are long and regular; such tiles do not fit a ring stage anyway)
     for (int q = tid; q < ((nz + 3) & ~3); q += PACK_T) bul[q] = q < nz ? bci[q] : 0;
     __syncthreads();
-    for (int q = tid; q < nz; q += PACK_T) bci[q] = q;
+    for (int q = tid; q < nz; q += PACK_T) bci[q] = split_local ? R + q : q;
   }
   if (wt == 0) for (int q = nz + tid; q < ((nz + 3) & ~3); q += PACK_T) bci[q] = 0;
   for (int i = tid; i < R + 4; i += PACK_T) hdr[i] = i <= R ? rpl[i] : (i == R + 1 ? nu : (i == R + 2 ? wt : 0));
@@ -224,9 +243,11 @@ __global__ void __launch_bounds__(PACK_T) pack_csr_tiles_kernel(const int *__res
 }
 
 void launch_pack_csr_tiles(const int *rp, const int *ci, const double *va, const int *perm, const int *inv,
-                           const long long *tile_off, int *tile_len, int *max_len_nu, unsigned char *blob, int n, cudaStream_t s) {
+                           const long long *tile_off, int *tile_len, int *max_len_nu, unsigned char *blob, int n,
+                           bool split_local, cudaStream_t s) {
   const int ntiles = (n + SWEEP_TILE_ROWS - 1) / SWEEP_TILE_ROWS;
-  pack_csr_tiles_kernel<<<ntiles, PACK_T, 0, s>>>(rp, ci, va, perm, inv, tile_off, tile_len, max_len_nu, blob, n);
+  pack_csr_tiles_kernel<<<ntiles, PACK_T, 0, s>>>(rp, ci, va, perm, inv, tile_off, tile_len, max_len_nu, blob, n,
+                                                  split_local ? 1 : 0);
 }
 
 // W, X, y in the internal ordering (row r = caller's observation perm[r], columns relabelled by inv; the entries of a row
@@ -799,6 +820,7 @@ void launch_sweep(const DeviceData &dd, int sm_count, cudaStream_t s) {
     gram_generic_kernel<<<296, 256, 0, s>>>(dd);
     return;
   }
+  if (dd.Xr != nullptr) { launch_sweep_sem(dd, sm_count, s); return; }   // SEM ring sweep (packed at create)
   if (dd.Zt != nullptr) {                       // packed at create iff the ring covers this design
     if (dd.d <= 6) launch_sweep_ring<1>(dd, sm_count, s);
     else if (dd.d <= 12) launch_sweep_ring<2>(dd, sm_count, s);

@@ -499,3 +499,67 @@ def test_chebyshev_against_exact_logdet_asymmetric():
     assert np.all(err[np.abs(v) <= 0.6] < 0.15)                 # probe noise ~ sqrt(2 / (N R)) per moment
     assert np.all(err < 1.0)                                    # measured ~0.25 at |v| = 0.9: small beside
     #                                                             the (N - M)/2 log rss term the MH ratio adds it to
+
+
+# ---------------------------------------------------------------------------
+# SEM ring sweep (csrc/semsweep.cu): de-duplicated row gathers + FP64 mma Gram update of [y | Wy | X | WX]
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("k,knn,n", [(4, 6, 3100), (9, 8, 4500), (13, 13, 4200), (20, 10, 9001), (22, 7, 2500)])
+def test_sem_ring_sweep_gram(k, knn, n, monkeypatch):
+    """2, 4 and 6 column groups of 8; slot-major tiles wider than the unrolled loop (kNN 13); a last tile that is not full.
+    The Gram matrix must match the oracle and (to rounding) the direct sweep of round 1, in the caller's ordering and in
+    the breadth-first one."""
+    capi = capi_mod()
+    p = _scrambled("sem", n, k, knn)
+    Wy, WX = core.spmm(p.W, p.y), core.spmm(p.W, p.X)
+    G_ref = core.gram(p.y, p.X, Wy, WX)
+    scale = np.sqrt(np.outer(np.diag(G_ref), np.diag(G_ref)))
+    got = {}
+    for ring, reorder in (("0", "1"), ("0", "0"), ("1", "1")):
+        monkeypatch.setenv("BSREG_NO_SEM_RING", ring)
+        monkeypatch.setenv("BSREG_REORDER", reorder)
+        with cuda_handle("sem", p, ldet=capi.LDET_CHEBYSHEV, cheb_order=8, cheb_probes=4) as h:
+            got[ring, reorder] = h.eval_gram()
+            assert np.array_equal(got[ring, reorder], h.eval_gram())
+        assert np.max(np.abs(got[ring, reorder] - G_ref) / scale) < 1e-13, (ring, reorder)
+    assert np.max(np.abs(got["0", "1"] - got["1", "1"]) / scale) < 1e-14
+
+
+def test_sem_ring_sweep_ragged_rows(monkeypatch):
+    """Empty rows, rows of very different length (CSR tile layout) and a row too long for a ring stage (the handle then
+    keeps the direct sweep): same Gram matrix, same chains."""
+    import scipy.sparse as sp
+    capi = capi_mod()
+    n = 4500
+    rng = np.random.default_rng(5)
+    p = make_problem("sem", n=n, k_reg=6, knn=5)
+    for long_row in (40, 1500):
+        W = p.W.tolil()
+        for i in (0, 63, 64, 1000, n - 1):
+            W.rows[i] = []; W.data[i] = []
+        cols = np.sort(rng.choice(n, long_row, replace=False))
+        W.rows[2000] = cols.tolist(); W.data[2000] = (np.full(long_row, 1.0 / long_row)).tolist()
+        W = sp_csr(sp.csr_matrix(W))
+        Wy, WX = core.spmm(W, p.y), core.spmm(W, p.X)
+        G_ref = core.gram(p.y, p.X, Wy, WX)
+        scale = np.sqrt(np.outer(np.diag(G_ref), np.diag(G_ref)))
+        for mode in ("0", "1"):
+            monkeypatch.setenv("BSREG_REORDER", mode)
+            with capi.Handle(p.y, p.X, model=capi.MODEL_SEM, W=W, ldet=capi.LDET_CHEBYSHEV, cheb_order=6, cheb_probes=2,
+                             n_chains=2, seed=1) as h:
+                assert np.max(np.abs(h.eval_gram() - G_ref) / scale) < 1e-13, (long_row, mode)
+                assert np.all(np.isfinite(h.run(5, 5)))
+
+
+def test_sem_ring_sweep_chains_follow_the_oracle():
+    """SEM at K = 20 (d = 42) in stream mode: every iteration's Gram matrix comes from the ring sweep."""
+    p = small_problem("sem", n=6000, k=20, knn=8)
+    capi = capi_mod()
+    with cuda_handle("sem", p, seed=17, n_chains=5, chain_offset=2, ldet=capi.LDET_CHEBYSHEV, cheb_order=16, cheb_probes=8) as h:
+        nodes = h.nodes()
+        got = h.run(25, 30)
+    ref = oracle_draws(oracle_chain("sem", p, seed=17, chain=2 + 3, nodes=nodes), 30, 25)
+    assert relnorm(got[3].T, ref) < 1e-7
+    with cuda_handle("sem", p, seed=17, n_chains=5, chain_offset=2, ldet=capi.LDET_CHEBYSHEV, cheb_order=16, cheb_probes=8,
+                     stats_mode=capi.STATS_CACHED) as h:
+        assert np.array_equal(h.run(25, 30), got)
