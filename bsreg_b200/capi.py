@@ -18,7 +18,7 @@ LIB_PATH = Path(os.environ.get("BSREG_CUDA_LIB") or Path(__file__).resolve().par
 
 MODEL_LM, MODEL_SAR, MODEL_SEM = 0, 1, 2
 PRIOR_INDEPENDENT, PRIOR_CONJUGATE, PRIOR_SHRINKAGE, PRIOR_HORSESHOE = 0, 1, 2, 3
-LDET_NONE, LDET_NODES, LDET_CHEBYSHEV = 0, 1, 2
+LDET_NONE, LDET_NODES, LDET_CHEBYSHEV, LDET_SPLINE = 0, 1, 2, 3
 STATS_STREAM, STATS_CACHED = 0, 1
 
 c_dp = C.POINTER(C.c_double)
@@ -45,6 +45,8 @@ class Options(C.Structure):
                 ("sp_lambda_a", C.c_double), ("sp_lambda_b", C.c_double), ("sp_lambda", C.c_double),
                 ("sp_lambda_scale", C.c_double), ("sp_lambda_min", C.c_double), ("sp_lambda_max", C.c_double),
                 ("cheb_order", C.c_int32), ("cheb_probes", C.c_int32),
+                ("ldet_grid_from", C.c_double), ("ldet_grid_to", C.c_double),
+                ("ldet_grid_len", C.c_int32), ("ldet_reps", C.c_int32),
                 ("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("seed", C.c_uint64),
                 ("n_devices", C.c_int32), ("devices", c_ip), ("stream", C.c_void_p)]
 
@@ -74,6 +76,8 @@ SYMBOLS = {
     "bsreg_eval_logdet": (C.c_int, [C.c_void_p, C.c_int32, c_dp, c_dp]),
     "bsreg_n_nodes": (C.c_int, [C.c_void_p]),
     "bsreg_get_nodes": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),
+    "bsreg_n_spline": (C.c_int, [C.c_void_p]),
+    "bsreg_get_spline": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "bsreg_eval_trace_moments": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, c_dp]),
     "bsreg_eval_conditionals": (C.c_int, [C.c_void_p, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp,
                                           c_dp, c_dp, c_dp, c_dp]),
@@ -132,7 +136,7 @@ class Handle:
     def __init__(self, y, X, *, model=MODEL_LM, prior=PRIOR_INDEPENDENT, W=None, X_slx=None, W_slx=None,
                  nodes=None, ldet=None, stats_mode=STATS_STREAM, n_chains=1, chain_offset=0, seed=0,
                  ng=None, sng=None, hs=None, spatial=None, cheb_order=50, cheb_probes=64,
-                 devices=None, stream=None):
+                 ldet_grid=(-1.0, 1.0 - 1e-12, 100), ldet_reps=1, devices=None, stream=None):
         lib = load()
         y = _f64(y).ravel()
         X = _f64(X, "F")
@@ -190,6 +194,8 @@ class Handle:
         opt.sp_lambda_a, opt.sp_lambda_b, opt.sp_lambda = sp_["lambda_a"], sp_["lambda_b"], sp_["lam"]
         opt.sp_lambda_scale, opt.sp_lambda_min, opt.sp_lambda_max = sp_["lambda_scale"], sp_["lambda_min"], sp_["lambda_max"]
         opt.cheb_order, opt.cheb_probes = cheb_order, cheb_probes
+        opt.ldet_grid_from, opt.ldet_grid_to, opt.ldet_grid_len = float(ldet_grid[0]), float(ldet_grid[1]), int(ldet_grid[2])
+        opt.ldet_reps = int(ldet_reps)
         opt.n_chains, opt.chain_offset, opt.seed = n_chains, chain_offset, seed
         if devices is not None:
             dv = np.ascontiguousarray(devices, dtype=np.int32)
@@ -297,6 +303,13 @@ class Handle:
         re, im, w = np.empty(nn), np.empty(nn), np.empty(nn)
         check(self._lib.bsreg_get_nodes(self._h, _dp(re), _dp(im), _dp(w)))
         return re, im, w
+
+    def spline(self):
+        """(x, y, b, c, d) of the grid + spline log-determinant (LDET_SPLINE)."""
+        nn = self._lib.bsreg_n_spline(self._h)
+        a = [np.empty(nn) for _ in range(5)]
+        check(self._lib.bsreg_get_spline(self._h, *[_dp(v) for v in a]))
+        return tuple(a)
 
     def eval_trace_moments(self, order, n_probes, seed):
         out = np.empty(order + 1)

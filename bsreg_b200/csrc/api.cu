@@ -175,6 +175,7 @@ struct bsreg_handle {
   std::atomic<int64_t> launches{0};   // shards are set up by one host thread each
   int64_t nnz = 0;
   std::vector<double> node_re, node_im, node_w;
+  std::vector<double> spline;         // BSREG_LDET_SPLINE: [x | y | b | c | d]
 };
 
 namespace {
@@ -761,6 +762,39 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   return BSREG_OK;
 }
 
+// Grid + spline log-determinant (R/15_sar.R:79-87): determinant grid on shard 0 (one CTA per grid point, dense LU with
+// partial pivoting), FMM coefficients on the host, the five arrays to every shard.
+int build_spline(bsreg_handle *h, const bsreg_options *o) {
+  const int G = o->ldet_grid_len, reps = o->ldet_reps > 0 ? o->ldet_reps : 1, size = h->n / reps;
+  std::vector<double> &sp = h->spline;
+  sp.assign((size_t)5 * G, 0.0);
+  for (int g = 0; g < G; ++g)                                   // i_seq, R/00_aux.R:105-107: from + (0:n1) * by
+    sp[g] = G == 1 ? o->ldet_grid_from : o->ldet_grid_from + (o->ldet_grid_to - o->ldet_grid_from) * g / (G - 1);
+  {
+    Shard &s = h->shards[0];
+    CU(cudaSetDevice(s.dev));
+    PoolTmp A(s.stream), xs(s.stream), out(s.stream);
+    CU(A.get((size_t)G * size * size * 8)); CU(xs.get((size_t)G * 8)); CU(out.get((size_t)G * 8));
+    TRY(upload(s, sp.data(), xs.p, (size_t)G * 8));
+    launch_grid_logdets(size, s.dd.rp, s.dd.ci, s.dd.va, G, xs.as<double>(), A.as<double>(), (double)reps, out.as<double>(), s.stream);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(sp.data() + G, out.p, (size_t)G * 8, cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+  }
+  fmm_spline_coefficients(G, sp.data(), sp.data() + G, sp.data() + 2 * G, sp.data() + 3 * G, sp.data() + 4 * G);
+  for (Shard &s : h->shards) {
+    CU(cudaSetDevice(s.dev));
+    double *d;
+    TRY(s.alloc(&d, (size_t)5 * G));
+    TRY(upload(s, sp.data(), d, (size_t)5 * G * 8));
+    CU(cudaStreamSynchronize(s.stream));
+    s.dd.spl_n = G; s.dd.spl = d;
+    s.dd.n_nodes = 0; s.dd.node_re = nullptr; s.dd.node_im = nullptr; s.dd.node_w = nullptr;
+  }
+  return BSREG_OK;
+}
+
 int init_chains(bsreg_handle *h, bool refresh_only) {
   const bsreg_options &o = h->opt;
   for (Shard &s : h->shards) {
@@ -843,6 +877,19 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
     delete h; return fail(BSREG_EINVAL, "BSREG_LDET_NODES needs node_re / node_w");
   }
 
+  if (h->spatial && o->ldet == BSREG_LDET_SPLINE) {
+    const int reps = o->ldet_reps > 0 ? o->ldet_reps : 1;
+    if (o->ldet_grid_len < 2 || !(o->ldet_grid_to > o->ldet_grid_from)) {
+      delete h; return fail(BSREG_EINVAL, "BSREG_LDET_SPLINE needs i_lambda = c(from, to, length) with to > from and length >= 2");
+    }
+    if (p->n % reps != 0) { delete h; return fail(BSREG_EINVAL, "'reps' must divide the number of observations"); }
+    if (p->n / reps > 4096) {
+      delete h;
+      return fail(BSREG_EINVAL, "BSREG_LDET_SPLINE factorises dense %d x %d matrices (limit 4096): use the eigenvalue or "
+                                "Chebyshev log-determinant at this size", p->n / reps, p->n / reps);
+    }
+  }
+
   Priors &pr = h->pr;
   pr.prior = o->prior;
   pr.shape0 = o->ng_shape; pr.rate0 = o->ng_rate; pr.shape1 = o->ng_shape + 0.5 * (double)p->n;   // R/10_lm.R:152
@@ -861,7 +908,7 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
   int rc = BSREG_OK, lo = 0;
   MomentsJob mjob;
   SharedOrder order;
-  const bool want_moments = h->spatial && o->ldet != BSREG_LDET_NODES;
+  const bool want_moments = h->spatial && o->ldet == BSREG_LDET_CHEBYSHEV;
   std::vector<int> cnts(ndev), los(ndev);
   for (int g = 0; g < ndev && rc == BSREG_OK; ++g) {
     Shard &s = h->shards[g];
@@ -893,7 +940,8 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
   pt.mark("shards total");
   // ---- log-determinant nodes ----
   if (rc == BSREG_OK && h->spatial) {
-    if (o->ldet == BSREG_LDET_NODES) {
+    if (o->ldet == BSREG_LDET_SPLINE) {
+    } else if (o->ldet == BSREG_LDET_NODES) {
       h->node_re.assign(p->node_re, p->node_re + p->n_nodes);
       if (p->node_im) h->node_im.assign(p->node_im, p->node_im + p->n_nodes); else h->node_im.assign(p->n_nodes, 0.0);
       h->node_w.assign(p->node_w, p->node_w + p->n_nodes);
@@ -904,7 +952,8 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
       else rc = trace_moments_dev(h, h->shards[0], p, order, probes, o->seed, mom.data());
       if (rc == BSREG_OK) chebyshev_nodes(mom, h->n, h->node_re, h->node_im, h->node_w);
     }
-    if (rc == BSREG_OK) rc = set_nodes(h);
+    if (rc == BSREG_OK && o->ldet == BSREG_LDET_SPLINE) rc = build_spline(h, o);
+    else if (rc == BSREG_OK) rc = set_nodes(h);
   }
   if (mjob.active) { std::vector<double> drop(mjob.order + 1); trace_moments_finish(h, h->shards[0], mjob, drop.data()); }   // error paths
   pt.mark("log-det nodes");
@@ -1171,7 +1220,7 @@ int bsreg_eval_residual_ss(bsreg_handle *h, int32_t n_eval, const double *beta, 
 int bsreg_eval_logdet(bsreg_handle *h, int32_t n_eval, const double *v, double *ldet) {
   if (!h || !v || !ldet || n_eval <= 0) return fail(BSREG_EINVAL, "bad argument");
   Shard &s = h->shards[0];
-  if (s.dd.n_nodes <= 0) return fail(BSREG_EINVAL, "handle has no log-determinant nodes");
+  if (s.dd.n_nodes <= 0 && s.dd.spl_n <= 0) return fail(BSREG_EINVAL, "handle has no log-determinant nodes");
   CU(cudaSetDevice(s.dev));
   double *dv, *dout;
   CU(pool_malloc((void **)&dv, (size_t)n_eval * 8)); CU(pool_malloc((void **)&dout, (size_t)n_eval * 8));
@@ -1186,6 +1235,17 @@ int bsreg_eval_logdet(bsreg_handle *h, int32_t n_eval, const double *v, double *
 }
 
 int bsreg_n_nodes(const bsreg_handle *h) { return h ? (int)h->node_re.size() : 0; }
+
+int bsreg_n_spline(const bsreg_handle *h) { return h ? (int)(h->spline.size() / 5) : 0; }
+
+int bsreg_get_spline(bsreg_handle *h, double *x, double *y, double *b, double *c, double *d) {
+  if (!h) return fail(BSREG_EINVAL, "null handle");
+  const size_t G = h->spline.size() / 5;
+  double *dst[5] = {x, y, b, c, d};
+  for (int k = 0; k < 5; ++k)
+    if (dst[k]) std::copy(h->spline.begin() + k * G, h->spline.begin() + (k + 1) * G, dst[k]);
+  return BSREG_OK;
+}
 
 int bsreg_get_nodes(bsreg_handle *h, double *re, double *im, double *w) {
   if (!h) return fail(BSREG_EINVAL, "null handle");

@@ -364,12 +364,17 @@ __global__ void __launch_bounds__(FAST_NT) chain_fast_kernel(DeviceData dd, Prio
     if (lane == 0) x[X_SD] = sqrt(sigma2);
     if (sar || sem) {
       const double prop = ph.truncated_rw(it, sar ? SLOT_LAMBDA_PROP : SLOT_RHO_PROP, lam, scale_l0, pr.lam_lo, pr.lam_hi);
-      double acc = 0.0;
-      for (int k = lane; k < dd.n_nodes; k += 32) {
-        const double aa = 1.0 - prop * dd.node_re[k], bb = prop * dd.node_im[k];
-        acc = fma(dd.node_w[k], 0.5 * log(aa * aa + bb * bb), acc);
+      double ldet_prop;
+      if (dd.spl_n > 0) {
+        ldet_prop = spline_ldet(dd, prop);
+      } else {
+        double acc = 0.0;
+        for (int k = lane; k < dd.n_nodes; k += 32) {
+          const double aa = 1.0 - prop * dd.node_re[k], bb = prop * dd.node_im[k];
+          acc = fma(dd.node_w[k], 0.5 * log(aa * aa + bb * bb), acc);
+        }
+        ldet_prop = warp_sum_c(acc);
       }
-      const double ldet_prop = warp_sum_c(acc);
       const double lp = lane == 0 ? log_prior_lambda(prop, pr) : log_prior_lambda(lam, pr);
       if (lane == 0) { x[X_PROP] = prop; x[X_LDETP] = ldet_prop; x[X_LPP] = lp; }
       if (lane == 1) x[X_LPC] = lp;

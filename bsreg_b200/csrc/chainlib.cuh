@@ -112,8 +112,21 @@ __device__ __forceinline__ double upper_dot(const double *Yrow, const double *w,
   return s0 + s1;
 }
 
+// FMM's SEVAL on the determinant grid (splinefun(pars, ldets)(lambda), R/15_sar.R:86-87): the piece of the largest knot
+// <= v; left of the grid the first piece, right of it the last knot's cubic
+__device__ __forceinline__ double spline_ldet(const DeviceData &dd, double v) {
+  const int n = dd.spl_n;
+  const double *x = dd.spl;
+  int lo = 0, hi = n;                                   // number of knots <= v
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (x[mid] <= v) lo = mid + 1; else hi = mid; }
+  const int i = lo > 0 ? (lo - 1 < n - 1 ? lo - 1 : n - 1) : 0;
+  const double dx = v - x[i];
+  return x[n + i] + dx * (x[2 * n + i] + dx * (x[3 * n + i] + dx * x[4 * n + i]));
+}
+
 template <int NT>
 __device__ double logdet_nodes(const DeviceData &dd, double v, double *red) {
+  if (dd.spl_n > 0) return spline_ldet(dd, v);          // uniform across the block: no reduction needed
   double acc = 0.0;
   for (int k = threadIdx.x; k < dd.n_nodes; k += NT) {
     const double a = 1.0 - v * dd.node_re[k], b = v * dd.node_im[k];

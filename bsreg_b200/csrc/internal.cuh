@@ -71,6 +71,9 @@ struct DeviceData {
   // log-determinant nodes
   int n_nodes;
   const double *node_re, *node_im, *node_w;
+  // grid + spline log-determinant (R/15_sar.R:79-87): spl = [x | y | b | c | d], spl_n knots each (0: nodes are used)
+  int spl_n;
+  const double *spl;
 };
 
 // entry (i, j) of the Gram matrix from the fixed-point buffer of this launch
@@ -147,6 +150,11 @@ void launch_probes(double *U, int n, int n_probes, uint64_t seed, cudaStream_t s
 void launch_dot(const double *a, const double *b, int64_t len, double *partial, double *out, cudaStream_t s);
 void launch_spmm_dot(int n, const int *rp, const int *ci, const double *va, const double *B, int m, double *out, double alpha,
                      const double *C, double beta, const double *U, double *partial, double *dot, cudaStream_t s);
+
+// launchers (logdet.cu)
+void launch_grid_logdets(int size, const int *rp, const int *ci, const double *va, int n_grid, const double *xs_dev,
+                         double *A, double reps, double *out, cudaStream_t s);
+void fmm_spline_coefficients(int n, const double *x, const double *y, double *b, double *c, double *d);
 
 // launchers (chain.cu)
 size_t chain_smem_bytes(int m, int model, int prior);

@@ -248,9 +248,6 @@ def ldet_nodes(W, ldet):
     """Nodes (re, im, weight) for `Re(sum(log(1 - lambda ev))) * reps`, R/15_sar.R:68-76,91-96.
     As in the reference a partial `ldet_*` list REPLACES the default list (`grid` missing = FALSE)."""
     reps = int(ldet.get("reps", 1) or 1)
-    if ldet.get("grid"):
-        raise NotImplementedError("ldet_*=list(grid=TRUE) (spline over a determinant grid, R/15_sar.R:79-87) is "
-                                  "not built yet; use the eigenvalue (default) or method='chebyshev' log-determinant")
     n = W.shape[0]
     size = n // reps
     if size * reps != n:
@@ -327,8 +324,15 @@ class Model:
         (eigenvalues with weight `reps`, or the Chebyshev nodes with weights folded from the Hutchinson trace moments,
         SURVEY App. B): sum_k w_k Re 1 / (1 - lam omega_k).  Replaces the dense
         `sum(diag(solve(diag(N) - lambda * W)))` of R/15_sar.R:145-146 (marked "To-do: ... more efficient" there)."""
-        re, im, w = self.handle.nodes()
         lam = np.atleast_1d(np.asarray(lam, dtype=np.float64))
+        x, y, b, c, d = self.handle.spline()
+        if len(x):
+            # grid + spline log-determinant: tr((I - lam W)^-1) = N + lam tr(W (I - lam W)^-1) = N - lam d/dlam log|I - lam W|,
+            # with the derivative of the same spline the sampler evaluates
+            i = np.clip(np.searchsorted(x, lam, side="right") - 1, 0, len(x) - 1)
+            dx = lam - x[i]
+            return self.handle.n - lam * (b[i] + dx * (2.0 * c[i] + dx * 3.0 * d[i]))
+        re, im, w = self.handle.nodes()
         z = 1.0 - lam[:, None] * (re[None, :] + 1j * im[None, :])
         return np.sum(w[None, :] * (1.0 / z).real, axis=1)
 
@@ -446,7 +450,11 @@ def get_model(type, y, X, options=None, Psi=None, X_SLX=None, Psi_SLX=None, ldet
         ld = (ldet_SAR if spatial == "SAR" else ldet_SEM)
         ld = dict(DEFAULT_LDET) if ld is None else dict(ld)
         method = ld.get("method", "eigen" if n <= EIGEN_MAX_N * int(ld.get("reps", 1) or 1) else "chebyshev")
-        if method == "eigen":
+        if ld.get("grid") is True:                                        # isTRUE(ldet$grid), R/15_sar.R:69
+            # spline over a determinant grid, R/15_sar.R:79-87: the dense LUs run on the device (BSREG_LDET_SPLINE)
+            i_lambda = ld.get("i_lambda", DEFAULT_LDET["i_lambda"])
+            kw.update(ldet=capi.LDET_SPLINE, ldet_grid=tuple(i_lambda), ldet_reps=int(ld.get("reps", 1) or 1))
+        elif method == "eigen":
             kw["nodes"] = ldet_nodes(W, ld)
         elif method == "chebyshev":
             kw.update(ldet=capi.LDET_CHEBYSHEV, cheb_order=int(ld.get("order", 50)), cheb_probes=int(ld.get("probes", 64)))

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BSREG_ABI_VERSION 1
+#define BSREG_ABI_VERSION 2
 
 enum { BSREG_OK = 0, BSREG_EINVAL = -1, BSREG_ECUDA = -2, BSREG_ENOMEM = -3,
        BSREG_EABORT = -4, BSREG_ENOGPU = -5 };
@@ -44,7 +44,11 @@ enum { BSREG_PRIOR_INDEPENDENT = 0, BSREG_PRIOR_CONJUGATE = 1,
        BSREG_PRIOR_SHRINKAGE = 2, BSREG_PRIOR_HORSESHOE = 3 };
 /* log|I - lambda W|: given nodes (eigenvalues, R/15_sar.R:91-96) or Chebyshev
  * moments estimated on the device from W (new at large N) */
-enum { BSREG_LDET_NONE = 0, BSREG_LDET_NODES = 1, BSREG_LDET_CHEBYSHEV = 2 };
+enum { BSREG_LDET_NONE = 0, BSREG_LDET_NODES = 1, BSREG_LDET_CHEBYSHEV = 2,
+       /* ldet_SAR / ldet_SEM = list(grid = TRUE): exact log|det(I - x W_sub)| * reps on a grid of x (dense LU on the
+        * device, the algorithm behind R's determinant()), interpolated by the FMM cubic spline of stats::splinefun
+        * (R/15_sar.R:79-87, R/15_sem.R:91-99, R/00_aux.R:105-107) */
+       BSREG_LDET_SPLINE = 3 };
 /* STREAM: W, y, X are swept every Gibbs iteration (fused SpMM + Gram reduction);
  * CACHED: the sweep runs once at create() -- same draws, see DESIGN.md */
 enum { BSREG_STATS_STREAM = 0, BSREG_STATS_CACHED = 1 };
@@ -84,6 +88,10 @@ typedef struct {
   double sp_lambda_a, sp_lambda_b, sp_lambda, sp_lambda_scale, sp_lambda_min, sp_lambda_max;
   /* BSREG_LDET_CHEBYSHEV */
   int32_t cheb_order, cheb_probes;
+  /* BSREG_LDET_SPLINE: i_lambda = c(from, to, length) and reps of ldet_SAR / ldet_SEM (R/15_sar.R:47); the grid
+   * matrices are the leading (n / reps) x (n / reps) block of W (get_W, R/15_sar.R:72-76), at most 4096 wide */
+  double ldet_grid_from, ldet_grid_to;
+  int32_t ldet_grid_len, ldet_reps;
   /* chains: this handle runs global chains [chain_offset, chain_offset + n_chains) */
   int32_t n_chains, chain_offset;
   uint64_t seed;
@@ -142,6 +150,10 @@ int  bsreg_eval_logdet(bsreg_handle *h, int32_t n_eval, const double *v, double 
 /* nodes in use (eigen nodes as given, or Chebyshev nodes built at create); arrays of bsreg_n_nodes() */
 int  bsreg_n_nodes(const bsreg_handle *h);
 int  bsreg_get_nodes(bsreg_handle *h, double *re, double *im, double *w);
+/* BSREG_LDET_SPLINE: the grid and the spline in use: x, y = log-determinants at the grid points, FMM coefficients b, c, d
+ * (s(u) = y_i + dx (b_i + dx (c_i + dx d_i)), dx = u - x_i); arrays of bsreg_n_spline() */
+int  bsreg_n_spline(const bsreg_handle *h);
+int  bsreg_get_spline(bsreg_handle *h, double *x, double *y, double *b, double *c, double *d);
 /* K4: Chebyshev trace moments m_0..m_order of W with n_probes Rademacher probes */
 int  bsreg_eval_trace_moments(bsreg_handle *h, int32_t order, int32_t n_probes, uint64_t seed, double *moments);
 /* conditional pieces at fixed parameters, per evaluation e:

@@ -210,8 +210,13 @@ class RefChain:
             self.MH["lambda"] = MHState(self.lam, float(sp_["lambda_scale"]))
             self.lam_a, self.lam_b = float(sp_["lambda_a"]), float(sp_["lambda_b"])
             self.lam_lo, self.lam_hi = float(sp_["lambda_min"]), float(sp_["lambda_max"])
+            self.spline = None
             if self.ldet.get("kind", "eigen") == "eigen":
                 self.nodes = core.eigen_nodes(self.W, int(self.ldet.get("reps", 1)))
+            elif self.ldet["kind"] == "spline":                # grid = TRUE, R/15_sar.R:79-87, R/15_sem.R:91-99
+                from .spline import SplineLogdet
+                self.spline = SplineLogdet(self.W, self.ldet.get("i_lambda", (-1.0, 1.0 - 1e-12, 100)),
+                                           int(self.ldet.get("reps", 1)))
             else:
                 self.nodes = (np.asarray(self.ldet["re"]), np.asarray(self.ldet["im"]), np.asarray(self.ldet["w"]))
         self._refresh()
@@ -305,6 +310,8 @@ class RefChain:
                 self.sng_theta = mh.value
 
     def _ldet(self, v):
+        if self.spline is not None:
+            return self.spline(v)
         return core.ldet_nodes(v, *self.nodes)
 
     def _sample_lambda(self, it):

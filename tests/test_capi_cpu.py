@@ -41,7 +41,7 @@ def test_library_exports_every_declared_symbol(capi):
         assert hasattr(lib, name), f"{name} declared in bsreg_cuda.h but not exported"
         assert name in capi.SYMBOLS, f"{name} has no ctypes prototype"
     assert sorted(capi.SYMBOLS) == names
-    assert lib.bsreg_abi_version() == 1
+    assert lib.bsreg_abi_version() == 2
 
 
 def test_ctypes_structs_match_the_c_layout(capi, tmp_path):

@@ -128,3 +128,19 @@ def test_spatial_effects_from_chebyshev_nodes():
     Wd = p.W.toarray()
     want = np.array([np.trace(np.linalg.inv(np.eye(1500) - v * Wd)) / 1500 for v in lam])
     assert np.max(np.abs(got - want)) < 5e-3         # Hutchinson error of 256 probes at N = 1500 (exact moments 0-2)
+
+
+def test_interface_grid_true_runs_the_spline_logdet(cig):
+    """`bsar(..., ldet_SAR = list(grid = TRUE, i_lambda = c(-1, 1 - 1e-12, 100), reps = 30))` on the cigarettes panel:
+    the reference's spline-over-a-determinant-grid option (R/15_sar.R:79-87).  Posterior of lambda close to the
+    eigenvalue-method fit; effects available through the spline's derivative."""
+    name, model, prior, pri, y, X, W, X_slx, reps = list(configs(cig))[1]
+    assert model == "sar"
+    kw = dict(type=model, W=W, options=bs.set_options(prior), n_save=300, n_burn=200, verbose=False, seed=5)
+    fit_e = bs.bm((y, X), ldet_SAR=dict(reps=reps), **kw)
+    fit_g = bs.bm((y, X), ldet_SAR=dict(grid=True, i_lambda=(-1, 1 - 1e-12, 100), reps=reps), **kw)
+    assert fit_g.model.handle.spline()[0].shape == (100,)
+    assert abs(fit_g.draws[:, -1].mean() - fit_e.draws[:, -1].mean()) < 0.05
+    eg, ee = fit_g.effects(), fit_e.effects()
+    assert np.allclose(eg["total"].mean(0), ee["total"].mean(0), rtol=0.1, atol=0.02)
+    assert np.allclose(eg["direct"].mean(0), ee["direct"].mean(0), rtol=0.1, atol=0.02)

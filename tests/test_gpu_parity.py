@@ -563,3 +563,50 @@ def test_sem_ring_sweep_chains_follow_the_oracle():
     with cuda_handle("sem", p, seed=17, n_chains=5, chain_offset=2, ldet=capi.LDET_CHEBYSHEV, cheb_order=16, cheb_probes=8,
                      stats_mode=capi.STATS_CACHED) as h:
         assert np.array_equal(h.run(25, 30), got)
+
+
+# ---------------------------------------------------------------------------
+# grid + spline log-determinant, ldet_* = list(grid = TRUE) (R/15_sar.R:79-87, R/15_sem.R:91-99): csrc/logdet.cu
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("symmetric,reps", [(True, 1), (False, 1), (True, 3)])
+def test_grid_spline_logdet(symmetric, reps):
+    """The determinant grid (dense LU with partial pivoting on the device, one CTA per grid point) against LAPACK's, the
+    FMM coefficients against the oracle's restatement, and the per-proposal evaluation -- 1e-8 on log-determinants."""
+    import scipy.sparse as sp
+    from oracle.spline import SplineLogdet, spline_eval
+    capi = capi_mod()
+    p = small_problem("sar", n=231, k=3, symmetric=symmetric)
+    W = sp_csr(sp.kron(sp.eye(reps), p.W)) if reps > 1 else p.W      # panel: kronecker(diag(reps), W), paper/0_data.R:27
+    y, X = np.tile(p.y, reps), np.tile(p.X, (reps, 1))
+    grid = (-1.0, 1.0 - 1e-12, 100)
+    with capi.Handle(y, X, model=capi.MODEL_SAR, W=W, ldet=capi.LDET_SPLINE, ldet_grid=grid, ldet_reps=reps, seed=2) as h:
+        x, ld, b, c, d = h.spline()
+        ref = SplineLogdet(W, grid, reps)
+        assert np.array_equal(x, ref.x)
+        fin = np.isfinite(ref.y)
+        assert np.array_equal(np.isfinite(ld), fin)
+        assert np.max(np.abs(ld[fin] - ref.y[fin]) / np.maximum(np.abs(ref.y[fin]), 1.0)) < 1e-8
+        if fin.all():
+            for got, want in ((b, ref.b), (c, ref.c), (d, ref.d)):
+                assert np.max(np.abs(got - want)) <= 1e-6 * np.max(np.abs(want))     # second differences of 1e-12 noise
+            v = np.array([-0.93, -0.4, 0.0, 0.31, 0.77, 0.985])
+            want = np.array([spline_eval(t, x, ld, b, c, d) for t in v])               # same coefficients: 1e-8
+            assert np.max(np.abs(h.eval_logdet(v) - want) / np.maximum(np.abs(want), 1.0)) < 1e-8
+            dense = np.array([core.ldet_dense(t, W) for t in v[:5]])
+            assert np.max(np.abs(h.eval_logdet(v[:5]) - dense)) < 5e-3 * reps * np.max(np.abs(dense))
+
+
+@pytest.mark.parametrize("model", ["sar", "sem"])
+def test_chain_with_grid_spline_logdet_matches_oracle(model):
+    capi = capi_mod()
+    p = small_problem(model, n=300, k=4)
+    grid = (-1.0, 1.0 - 1e-12, 60)
+    with capi.Handle(p.y, p.X, model=MODEL_CODE_[model], W=p.W, ldet=capi.LDET_SPLINE, ldet_grid=grid, seed=77,
+                     n_chains=3, chain_offset=4) as h:
+        got = h.run(40, 50)
+    from oracle.sampler import PhiloxRNG, RefChain, sample
+    ref = sample(RefChain(model, p.y, p.X, W=p.W, ldet=dict(kind="spline", i_lambda=grid, reps=1), rng=PhiloxRNG(77, 5)), 50, 40)
+    assert relnorm(got[1].T, ref) < 1e-7
+
+
+MODEL_CODE_ = {"sar": 1, "sem": 2}

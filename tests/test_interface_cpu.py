@@ -95,8 +95,8 @@ def test_errors_that_precede_device_work():
                 options=bs.set_options(SLX=bs.set_SLX(delta_scale=0.1)), verbose=False)
     with pytest.raises(ValueError, match="should be one of"):
         bs.bm((y, X), type="probit")
-    with pytest.raises(NotImplementedError, match="grid"):
-        bi.ldet_nodes(bi._as_csr(np.eye(4) * 0.0 + np.diag(np.ones(3), 1), 4, "Psi_SAR"), dict(grid=True))
+    with pytest.raises(ValueError, match="'reps' must divide"):
+        bi.ldet_nodes(bi._as_csr(np.eye(4) * 0.0 + np.diag(np.ones(3), 1), 4, "Psi_SAR"), dict(reps=3))
 
 
 def test_ldet_nodes_reps_and_symmetry():
