@@ -28,28 +28,47 @@ static void handle_finalizer(SEXP ptr) {
   if (h) { bsreg_destroy(h); R_ClearExternalPtr(ptr); }
 }
 
-/* .Call("C_bsreg_create", y, X, X_slx, W_p, W_i, W_x (dgRMatrix slots, 0-based), nodes (list re, im, w or NULL),
- *       model, prior, priors (the `priors` list of set_options()), n_chains, seed)                                  */
-SEXP C_bsreg_create(SEXP y, SEXP X, SEXP X_slx, SEXP Wp, SEXP Wj, SEXP Wx, SEXP nodes, SEXP model, SEXP prior,
-                    SEXP priors, SEXP n_chains, SEXP seed) {
+static SEXP elt(SEXP list, const char *name) {
+  SEXP names = Rf_getAttrib(list, R_NamesSymbol);
+  for (R_xlen_t i = 0; i < XLENGTH(list); ++i)
+    if (strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return VECTOR_ELT(list, i);
+  return R_NilValue;
+}
+
+/* .Call("C_bsreg_create", y, X, X_slx, W, W_slx (lists p, j, x: dgRMatrix slots, 0-based; or NULL),
+ *       nodes (list re, im, w or NULL), model, prior, priors (the `priors` list of set_options(), by name),
+ *       ldet (kind, reps, cached), grid (from, to, length), n_chains, seed, devices (integer or NULL))                 */
+SEXP C_bsreg_create(SEXP y, SEXP X, SEXP X_slx, SEXP W, SEXP W_slx, SEXP nodes, SEXP model, SEXP prior, SEXP priors,
+                    SEXP ldet, SEXP grid, SEXP n_chains, SEXP seed, SEXP devices) {
   bsreg_problem p; bsreg_options o;
   memset(&p, 0, sizeof p); memset(&o, 0, sizeof o);
   p.n = Rf_nrows(X); p.k = Rf_ncols(X); p.y = REAL(y); p.X = REAL(X);              /* column-major, as R stores it */
   if (!Rf_isNull(X_slx)) { p.k_slx = Rf_ncols(X_slx); p.X_slx = REAL(X_slx); }
-  if (!Rf_isNull(Wp)) { p.nnz = XLENGTH(Wx); p.row_ptr = INTEGER(Wp); p.col_idx = INTEGER(Wj); p.val = REAL(Wx); }
+  if (!Rf_isNull(W)) {
+    p.nnz = XLENGTH(elt(W, "x")); p.row_ptr = INTEGER(elt(W, "p")); p.col_idx = INTEGER(elt(W, "j")); p.val = REAL(elt(W, "x"));
+  }
+  if (!Rf_isNull(W_slx)) {                                                         /* separate Psi_SLX, R/40_setup.R:99 */
+    p.nnz_slx = XLENGTH(elt(W_slx, "x")); p.row_ptr_slx = INTEGER(elt(W_slx, "p"));
+    p.col_idx_slx = INTEGER(elt(W_slx, "j")); p.val_slx = REAL(elt(W_slx, "x"));
+  }
   if (!Rf_isNull(nodes)) {
     p.n_nodes = (int32_t)XLENGTH(VECTOR_ELT(nodes, 0));
     p.node_re = REAL(VECTOR_ELT(nodes, 0)); p.node_im = REAL(VECTOR_ELT(nodes, 1)); p.node_w = REAL(VECTOR_ELT(nodes, 2));
   }
   o.model = Rf_asInteger(model); o.prior = Rf_asInteger(prior);
-  o.ldet = o.model == BSREG_MODEL_LM ? BSREG_LDET_NONE : (Rf_isNull(nodes) ? BSREG_LDET_CHEBYSHEV : BSREG_LDET_NODES);
-  o.stats_mode = BSREG_STATS_STREAM;
-  SEXP NG = VECTOR_ELT(priors, 0), SNG = VECTOR_ELT(priors, 1), HS = VECTOR_ELT(priors, 2);
-  SEXP SP = VECTOR_ELT(priors, o.model == BSREG_MODEL_SEM ? 5 : 3);                /* "SEM" or "SAR", R/41_set_options.R:29-31 */
-  SEXP mu = VECTOR_ELT(NG, 0), prec = VECTOR_ELT(NG, 1);
+  o.ldet = INTEGER(ldet)[0]; o.ldet_reps = INTEGER(ldet)[1];
+  o.stats_mode = INTEGER(ldet)[2] ? BSREG_STATS_CACHED : BSREG_STATS_STREAM;
+  o.ldet_grid_from = REAL(grid)[0]; o.ldet_grid_to = REAL(grid)[1]; o.ldet_grid_len = (int32_t)REAL(grid)[2];
+  SEXP NG = elt(priors, "NG"), SNG = elt(priors, "SNG"), HS = elt(priors, "HS");
+  SEXP SP = elt(priors, o.model == BSREG_MODEL_SEM ? "SEM" : "SAR");               /* R/41_set_options.R:29-31 */
+  SEXP mu = elt(NG, "mu"), prec = elt(NG, "precision"), beta0 = elt(NG, "beta");
   o.ng_mu = REAL(mu); o.ng_mu_len = (int32_t)XLENGTH(mu);
-  o.ng_precision = REAL(prec); o.ng_precision_len = (int32_t)XLENGTH(prec);
+  o.ng_precision = REAL(prec); o.ng_precision_len = (int32_t)XLENGTH(prec);       /* a scalar or the diagonal */
   o.ng_shape = num(NG, "shape", 0.01); o.ng_rate = num(NG, "rate", 0.01); o.ng_sigma0 = num(NG, "sigma", R_NaN);
+  if (!Rf_isNull(beta0)) {                                                         /* starting beta, R/10_lm.R:158-160 */
+    if (XLENGTH(beta0) != p.k + p.k_slx) Rf_error("Please provide a valid starting value for 'beta' (one per coefficient).");
+    o.ng_beta0 = REAL(beta0);
+  }
   o.sng_lambda_a = num(SNG, "lambda_a", 0.01); o.sng_lambda_b = num(SNG, "lambda_b", 0.01);
   o.sng_theta_scale = num(SNG, "theta_scale", 0); o.sng_theta_a = num(SNG, "theta_a", 1);
   o.sng_lambda = num(SNG, "lambda", 1); o.sng_tau = num(SNG, "tau", 10); o.sng_theta = num(SNG, "theta", 0.1);
@@ -59,6 +78,7 @@ SEXP C_bsreg_create(SEXP y, SEXP X, SEXP X_slx, SEXP Wp, SEXP Wj, SEXP Wx, SEXP 
   o.sp_lambda_max = num(SP, "lambda_max", 1 - 1e-12);
   o.cheb_order = 50; o.cheb_probes = 64;
   o.n_chains = Rf_asInteger(n_chains); o.seed = (uint64_t)Rf_asReal(seed);
+  if (!Rf_isNull(devices)) { o.n_devices = (int32_t)XLENGTH(devices); o.devices = INTEGER(devices); }   /* chains split over GPUs */
   bsreg_handle *h = NULL;
   if (bsreg_create(&p, &o, &h) != BSREG_OK) Rf_error("bsreg_cuda: %s", bsreg_last_error());
   SEXP ptr = PROTECT(R_MakeExternalPtr(h, R_NilValue, R_NilValue));
@@ -111,7 +131,7 @@ SEXP C_bsreg_state(SEXP ptr) {
 }
 
 static const R_CallMethodDef call_methods[] = {
-  {"C_bsreg_create", (DL_FUNC)&C_bsreg_create, 12},
+  {"C_bsreg_create", (DL_FUNC)&C_bsreg_create, 14},
   {"C_bsreg_run", (DL_FUNC)&C_bsreg_run, 4},
   {"C_bsreg_state", (DL_FUNC)&C_bsreg_state, 1},
   {NULL, NULL, 0}};
