@@ -16,6 +16,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/bsreg_cuda.h"
 #include "internal.cuh"
 
@@ -25,11 +27,26 @@ namespace {
 
 thread_local std::string g_err;
 
-// BSREG_TIMING=1: wall-clock of the create() phases on stderr (diagnostics only)
+// NVTX range (nsys / ncu --nvtx timelines): create phases, run blocks
+struct Nvtx {
+  explicit Nvtx(const char *name) { nvtxRangePushA(name); }
+  ~Nvtx() { nvtxRangePop(); }
+  Nvtx(const Nvtx &) = delete;
+  Nvtx &operator=(const Nvtx &) = delete;
+};
+
+// BSREG_TIMING=1: wall-clock of the create() phases on stderr (diagnostics only); every phase is also an NVTX range
 struct PhaseTimer {
-  bool on = getenv("BSREG_TIMING") != nullptr;
+  bool on = getenv("BSREG_TIMING") != nullptr, open = false;
   std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  ~PhaseTimer() { if (open) nvtxRangePop(); }
+  void begin(const char *what) {
+    if (open) nvtxRangePop();
+    nvtxRangePushA(what);
+    open = true;
+  }
   void mark(const char *what) {
+    if (open) { nvtxRangePop(); open = false; }
     if (!on) return;
     cudaDeviceSynchronize();
     const auto now = std::chrono::steady_clock::now();
@@ -504,6 +521,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   dd.n = n; dd.m = m; dd.d = d; dd.model = h->model; dd.nnz = p->nnz;
 
   PhaseTimer pt;
+  pt.begin("bsreg_create: W upload");
   // ---- W (CSR) ----
   int *rp = nullptr, *ci = nullptr; double *va = nullptr;
   if (p->nnz > 0 || h->model != BSREG_MODEL_LM || p->k_slx > 0) {
@@ -529,6 +547,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   }
 
   pt.mark("W upload");
+  pt.begin("bsreg_create: y, X upload + transpose");
   // ---- y, X (column-major on the host -> row-major [n][m] in HBM) ----
   double *y, *X;
   TRY(s.alloc(&y, (size_t)n)); TRY(s.alloc(&X, (size_t)n * m));
@@ -565,6 +584,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   dd.y = y; dd.X = X;
   h->launches += 1;
   pt.mark("y, X upload + transpose");
+  pt.begin("bsreg_create: tile packing");
   // ---- tile-blocked operands of the ring sweep (sweep.cu): Zt and the per-tile CSR blobs ----
   dd.Zt = nullptr; dd.Xr = nullptr; dd.tile_ul = nullptr; dd.csr_blob = nullptr; dd.tile_off = nullptr; dd.tile_len = nullptr; dd.yp = y;
   dd.tile_max_blob = 0; dd.tile_max_nu = 0;
@@ -696,6 +716,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   }
 
   pt.mark("tile packing");
+  pt.begin("bsreg_create: lags, scales, first sweep");
   // ---- cached lags (R/15_sar.R:57, R/15_sem.R:63-64) ----
   dd.Wy = nullptr; dd.WX = nullptr;
   if (h->model != BSREG_MODEL_LM) {
@@ -735,6 +756,7 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   enqueue_sweep(h, s, s.stream);
 
   pt.mark("lags, scales, first sweep");
+  pt.begin("bsreg_create: chain state");
   // ---- chain state ----
   ChainState &cs = s.cs;
   cs.n_chains = n_chains; cs.chain_offset = o->chain_offset + chain_lo; cs.seed = o->seed;
@@ -853,6 +875,7 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
     }
   }
   if (p->k_slx > 0 && !p->X_slx) return fail(BSREG_EINVAL, "k_slx > 0 needs X_slx");
+  Nvtx range_create("bsreg_create");
   PhaseTimer pt0;
   int ndev_avail = 0;
   if (cudaGetDeviceCount(&ndev_avail) != cudaSuccess || ndev_avail == 0) {
@@ -938,6 +961,7 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
     }
   }
   pt.mark("shards total");
+  pt.begin("bsreg_create: log-determinant");
   // ---- log-determinant nodes ----
   if (rc == BSREG_OK && h->spatial) {
     if (o->ldet == BSREG_LDET_SPLINE) {
@@ -957,6 +981,7 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
   }
   if (mjob.active) { std::vector<double> drop(mjob.order + 1); trace_moments_finish(h, h->shards[0], mjob, drop.data()); }   // error paths
   pt.mark("log-det nodes");
+  pt.begin("bsreg_create: chain init");
   if (rc == BSREG_OK) rc = init_chains(h, false);
   pt.mark("chain init");
   cudaSetDevice(cur);
@@ -1011,6 +1036,7 @@ int bsreg_run(bsreg_handle *h, int32_t n_burn, int32_t n_save, const bsreg_mh *m
               bsreg_progress_fn progress, void *user) {
   if (!h) return fail(BSREG_EINVAL, "null handle");
   if (n_burn < 0 || n_save < 0) return fail(BSREG_EINVAL, "n_burn and n_save must be non-negative");
+  Nvtx range_run("bsreg_run");
   const bsreg_mh def{0.8, 0.20, 0.45, 0.8};
   if (!mh) mh = &def;
   int cur = 0;
@@ -1042,6 +1068,7 @@ int bsreg_run(bsreg_handle *h, int32_t n_burn, int32_t n_save, const bsreg_mh *m
   while (done < total && rc == BSREG_OK) {
     int nb;
     const bool saving = done >= n_burn;
+    Nvtx range_block(saving ? "bsreg_run: sampling block" : "bsreg_run: burn-in block");
     if (!saving) nb = (int)std::min<int64_t>(BLOCK_ITERS, n_burn - done);
     else nb = (int)std::min<int64_t>(BLOCK_ITERS, total - done);
     for (Shard &s : h->shards) {

@@ -216,7 +216,7 @@ class RefChain:
             elif self.ldet["kind"] == "spline":                # grid = TRUE, R/15_sar.R:79-87, R/15_sem.R:91-99
                 from .spline import SplineLogdet
                 self.spline = SplineLogdet(self.W, self.ldet.get("i_lambda", (-1.0, 1.0 - 1e-12, 100)),
-                                           int(self.ldet.get("reps", 1)))
+                                           int(self.ldet.get("reps", 1)), self.ldet.get("values"))
             else:
                 self.nodes = (np.asarray(self.ldet["re"]), np.asarray(self.ldet["im"]), np.asarray(self.ldet["w"]))
         self._refresh()

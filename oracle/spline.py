@@ -100,8 +100,10 @@ def grid_logdets(W, i_lambda=(-1.0, 1.0 - 1e-12, 100), reps: int = 1):
 class SplineLogdet:
     """get_ldet of the grid branch: splinefun(pars, ldets)(lambda)."""
 
-    def __init__(self, W, i_lambda=(-1.0, 1.0 - 1e-12, 100), reps: int = 1):
-        self.x, self.y = grid_logdets(W, i_lambda, reps)
+    def __init__(self, W, i_lambda=(-1.0, 1.0 - 1e-12, 100), reps: int = 1, values=None):
+        # values = (x, y): a determinant grid computed elsewhere (tests: the device's, so that both sides interpolate the
+        # same numbers -- at a nearly singular grid point two LUs agree to ~1e-4 only)
+        self.x, self.y = grid_logdets(W, i_lambda, reps) if values is None else (np.asarray(values[0]), np.asarray(values[1]))
         self.b, self.c, self.d = fmm_coefficients(self.x, self.y)
 
     def __call__(self, lam: float) -> float:
