@@ -13,7 +13,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIB = ROOT / "lib" / "libbsreg_cuda.so"
-SOURCES = ["api.cu", "sweep.cu", "semsweep.cu", "logdet.cu", "chain.cu", "persist.cu"]
+SOURCES = ["api.cu", "sweep.cu", "semsweep.cu", "logdet.cu", "slxdelta.cu", "chain.cu", "persist.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

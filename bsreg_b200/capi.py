@@ -47,6 +47,9 @@ class Options(C.Structure):
                 ("cheb_order", C.c_int32), ("cheb_probes", C.c_int32),
                 ("ldet_grid_from", C.c_double), ("ldet_grid_to", C.c_double),
                 ("ldet_grid_len", C.c_int32), ("ldet_reps", C.c_int32),
+                ("slx_psi", C.c_int32), ("slx_psi_norm", C.c_int32),
+                ("slx_delta", C.c_double), ("slx_delta_scale", C.c_double), ("slx_delta_a", C.c_double),
+                ("slx_delta_b", C.c_double), ("slx_delta_min", C.c_double), ("slx_delta_max", C.c_double),
                 ("n_chains", C.c_int32), ("chain_offset", C.c_int32), ("seed", C.c_uint64),
                 ("n_devices", C.c_int32), ("devices", c_ip), ("stream", C.c_void_p)]
 
@@ -70,6 +73,8 @@ SYMBOLS = {
     "bsreg_aux_len": (C.c_int, [C.c_void_p]),
     "bsreg_get_state": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_lp, c_lp]),
     "bsreg_set_state": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_lp, c_lp]),
+    "bsreg_get_delta_state": (C.c_int, [C.c_void_p, c_dp, c_dp, c_lp]),
+    "bsreg_set_delta_state": (C.c_int, [C.c_void_p, c_dp, c_dp, c_lp]),
     "bsreg_eval_spmm": (C.c_int, [C.c_void_p, c_dp, C.c_int32, c_dp]),
     "bsreg_eval_gram": (C.c_int, [C.c_void_p, c_dp]),
     "bsreg_eval_residual_ss": (C.c_int, [C.c_void_p, C.c_int32, c_dp, c_dp, c_dp, c_dp]),
@@ -136,7 +141,9 @@ class Handle:
     def __init__(self, y, X, *, model=MODEL_LM, prior=PRIOR_INDEPENDENT, W=None, X_slx=None, W_slx=None,
                  nodes=None, ldet=None, stats_mode=STATS_STREAM, n_chains=1, chain_offset=0, seed=0,
                  ng=None, sng=None, hs=None, spatial=None, cheb_order=50, cheb_probes=64,
-                 ldet_grid=(-1.0, 1.0 - 1e-12, 100), ldet_reps=1, devices=None, stream=None):
+                 ldet_grid=(-1.0, 1.0 - 1e-12, 100), ldet_reps=1, slx_psi=None, devices=None, stream=None):
+        """slx_psi: dict(normalise="row"|"none", delta=, delta_scale=, delta_a=, delta_b=, delta_min=, delta_max=) makes
+        W_slx (or W) a pattern of DISTANCES and Psi_SLX(delta) = dist ^ -delta a connectivity function."""
         lib = load()
         y = _f64(y).ravel()
         X = _f64(X, "F")
@@ -196,6 +203,13 @@ class Handle:
         opt.cheb_order, opt.cheb_probes = cheb_order, cheb_probes
         opt.ldet_grid_from, opt.ldet_grid_to, opt.ldet_grid_len = float(ldet_grid[0]), float(ldet_grid[1]), int(ldet_grid[2])
         opt.ldet_reps = int(ldet_reps)
+        if slx_psi is not None:
+            sp2 = dict(normalise="row", delta=1.0, delta_scale=0.0, delta_a=1.01, delta_b=1.01, delta_min=1e-12,
+                       delta_max=math.inf) | slx_psi
+            opt.slx_psi, opt.slx_psi_norm = 1, 1 if sp2["normalise"] == "row" else 0
+            opt.slx_delta, opt.slx_delta_scale = sp2["delta"], sp2["delta_scale"]
+            opt.slx_delta_a, opt.slx_delta_b = sp2["delta_a"], sp2["delta_b"]
+            opt.slx_delta_min, opt.slx_delta_max = sp2["delta_min"], sp2["delta_max"]
         opt.n_chains, opt.chain_offset, opt.seed = n_chains, chain_offset, seed
         if devices is not None:
             dv = np.ascontiguousarray(devices, dtype=np.int32)
@@ -264,6 +278,16 @@ class Handle:
                                         _dp(st["mh_scale"]), st["mh_counters"].ctypes.data_as(c_lp),
                                         st["iterations"].ctypes.data_as(c_lp)))
         return st
+
+    def get_delta_state(self):
+        Cn = self.n_chains
+        st = dict(delta=np.empty(Cn), scale=np.empty(Cn), counters=np.empty((Cn, 4), dtype=np.int64))
+        check(self._lib.bsreg_get_delta_state(self._h, _dp(st["delta"]), _dp(st["scale"]), st["counters"].ctypes.data_as(c_lp)))
+        return st
+
+    def set_delta_state(self, st):
+        a = {k: np.ascontiguousarray(v) for k, v in st.items()}
+        check(self._lib.bsreg_set_delta_state(self._h, _dp(a["delta"]), _dp(a["scale"]), a["counters"].ctypes.data_as(c_lp)))
 
     def set_state(self, st):
         a = {k: np.ascontiguousarray(v) for k, v in st.items()}

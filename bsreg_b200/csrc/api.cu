@@ -168,6 +168,8 @@ struct Shard {
   int save_cap = 0;
   double *p0_init = nullptr, *beta0 = nullptr;
   double *scratch = nullptr;          // partial sums for deterministic reductions
+  DeltaData dl{};                     // sampled SLX connectivity parameter (dl.L > 0: Psi_SLX is a function of delta)
+  double *dl_partial = nullptr;       // per-CTA partials of the per-chain sweep
   bool no_coop = false, coop_checked = false;   // the cooperative (persistent) launch was refused on this device
   cudaGraphExec_t graph = nullptr, sweep_graph = nullptr, chain_graph = nullptr;
 
@@ -185,7 +187,7 @@ struct Shard {
 
 struct bsreg_handle {
   int n = 0, k = 0, m = 0, d = 0, P = 0, model = 0, prior = 0, ldet = 0, stats_mode = 0, n_chains = 0;
-  bool spatial = false;
+  bool spatial = false, slx_psi = false;
   Priors pr{};
   bsreg_options opt{};
   std::vector<Shard> shards;
@@ -285,7 +287,10 @@ static cudaError_t launch_persistent_checked(bsreg_handle *h, Shard &s, const Ru
   return e;
 }
 
+int enqueue_iterations_delta(bsreg_handle *h, Shard &s, int count);
+
 int enqueue_iterations(bsreg_handle *h, Shard &s, int count, const RunCtl &ctl) {
+  if (s.dl.L > 0) return enqueue_iterations_delta(h, s, count);
   const bool streamed = h->stats_mode == BSREG_STATS_STREAM;
   if (count >= 3 && !s.no_coop && persistent_supported(s.dd, h->pr, s.cs.n_chains, s.sm_count)) {
     // one cooperative launch for the whole block: sweep CTAs and chain CTAs meet at the triple-buffered Gram matrix
@@ -556,7 +561,30 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   TRY(upload(s, p->y, y, (size_t)n * 8));
   TRY(upload(s, p->X, tmp.as<double>(), (size_t)n * k * 8));
   launch_transpose(tmp.as<double>(), X, n, k, m, 0, s.stream);
-  if (p->k_slx > 0) {   // setup_2SLX fixed-W branch, R/12_slx.R:60-68: X <- [X, Psi_SLX %*% X_SLX]
+  if (p->k_slx > 0 && o->slx_psi) {
+    // setup_2SLX with a connectivity FUNCTION (R/12_slx.R:69-74): pattern, log distances and X_SLX stay on the device;
+    // the lag columns of the design start at Psi(delta0) X_SLX (set_delta(priors$delta))
+    const int64_t nz = p->nnz_slx > 0 ? p->nnz_slx : p->nnz;
+    const int32_t *hrp = p->nnz_slx > 0 ? p->row_ptr_slx : p->row_ptr, *hci = p->nnz_slx > 0 ? p->col_idx_slx : p->col_idx;
+    const double *hva = p->nnz_slx > 0 ? p->val_slx : p->val;
+    std::vector<double> logd((size_t)nz);
+    for (int64_t q = 0; q < nz; ++q) logd[q] = std::log(hva[q]);
+    int *drp, *dci; double *dlog, *dxl;
+    TRY(s.alloc(&drp, (size_t)n + 1)); TRY(s.alloc(&dci, (size_t)nz)); TRY(s.alloc(&dlog, (size_t)nz));
+    TRY(s.alloc(&dxl, (size_t)n * p->k_slx));
+    CU(cudaStreamSynchronize(s.stream));                       // tmp is reused for X_SLX
+    TRY(upload(s, hrp, drp, ((size_t)n + 1) * 4)); TRY(upload(s, hci, dci, (size_t)nz * 4));
+    TRY(upload(s, logd.data(), dlog, (size_t)nz * 8));
+    TRY(upload(s, p->X_slx, tmp.as<double>(), (size_t)n * p->k_slx * 8));
+    launch_transpose(tmp.as<double>(), dxl, n, p->k_slx, p->k_slx, 0, s.stream);
+    DeltaData &dl = s.dl;
+    dl.L = p->k_slx; dl.norm = o->slx_psi_norm; dl.sampled = o->slx_delta_scale > 0.0 ? 1 : 0;
+    dl.rp = drp; dl.ci = dci; dl.logd = dlog; dl.Xl = dxl;
+    dl.prior_a = o->slx_delta_a; dl.prior_b = o->slx_delta_b; dl.lo = o->slx_delta_min; dl.hi = o->slx_delta_max;
+    launch_slx_power_lag(dl, o->slx_delta, X, m, k, n, s.stream);
+    CU(cudaStreamSynchronize(s.stream));                       // `logd` is a host temporary
+    h->launches += 2;
+  } else if (p->k_slx > 0) {   // setup_2SLX fixed-W branch, R/12_slx.R:60-68: X <- [X, Psi_SLX %*% X_SLX]
     const int *rps = rp, *cis = ci; const double *vas = va;
     PoolTmp xs_rm(s.stream), trp(s.stream), tci(s.stream), tva(s.stream);
     CU(cudaStreamSynchronize(s.stream));
@@ -817,6 +845,49 @@ int build_spline(bsreg_handle *h, const bsreg_options *o) {
   return BSREG_OK;
 }
 
+// Sampled SLX connectivity parameter: per-chain state (delta, proposal scale, counters) and per-chain Gram matrices, all
+// starting from the shared Gram matrix at delta0 (the design was built at Psi(delta0), setup_shard)
+int init_delta(bsreg_handle *h, const bsreg_options *o) {
+  for (Shard &s : h->shards) {
+    if (s.dl.L == 0) continue;
+    CU(cudaSetDevice(s.dev));
+    const int C = s.cs.n_chains, d = h->d, L = s.dl.L;
+    TRY(s.alloc(&s.dl.delta, (size_t)C)); TRY(s.alloc(&s.dl.delta_prop, (size_t)C)); TRY(s.alloc(&s.dl.scale, (size_t)C));
+    TRY(s.alloc(&s.dl.cnt, (size_t)C * 4)); TRY(s.alloc(&s.dl.Gchain, (size_t)C * d * d));
+    TRY(s.alloc(&s.dl_partial, (size_t)delta_sweep_ctas(s.sm_count) * C * L * (1 + h->m)));
+    std::vector<double> v((size_t)C, o->slx_delta), sc((size_t)C, o->slx_delta_scale);
+    TRY(upload(s, v.data(), s.dl.delta, (size_t)C * 8)); TRY(upload(s, v.data(), s.dl.delta_prop, (size_t)C * 8));
+    TRY(upload(s, sc.data(), s.dl.scale, (size_t)C * 8));
+    CU(cudaMemsetAsync(s.dl.cnt, 0, (size_t)C * 4 * 8, s.stream));
+    s.dd.gcur = (int)((s.seq + 2) % 3);
+    launch_gram_to_double(s.dd, s.dl.Gchain, s.stream);
+    for (int c = 1; c < C; ++c)
+      CU(cudaMemcpyAsync(s.dl.Gchain + (size_t)c * d * d, s.dl.Gchain, (size_t)d * d * 8, cudaMemcpyDeviceToDevice, s.stream));
+    ++h->launches;
+    CU(cudaStreamSynchronize(s.stream));                  // host temporaries
+    s.dd.Gchain = s.dl.Gchain;
+  }
+  return BSREG_OK;
+}
+
+// One Gibbs iteration with a sampled delta: proposals -> per-chain sweep (the lags at every chain's proposal) ->
+// sigma^2, beta, shrinkage (chain kernel on the chain's own Gram matrix) -> MH decision, tuning, draw store
+int enqueue_iterations_delta(bsreg_handle *h, Shard &s, int count) {
+  const int m = h->m, L = s.dl.L, parts = delta_sweep_ctas(s.sm_count);
+  for (int i = 0; i < count; ++i) {
+    if (s.dl.sampled) {
+      launch_delta_propose(s.dl, s.cs, s.stream);
+      launch_sweep_delta(s.dl, s.dd.X, s.dd.y, h->n, m, m - L, s.cs.n_chains, s.dl.delta_prop, s.dl_partial, s.sm_count, s.stream);
+      h->launches += 2;
+    }
+    enqueue_chain_step(h, s, s.stream);
+    launch_delta_decide(s.dd, s.dl, h->pr, s.cs, s.ctl_dev, s.draws_dev, s.dl_partial, parts, s.dl.sampled ? 0 : 2, s.stream);
+    ++h->launches;
+  }
+  CU(cudaGetLastError());
+  return BSREG_OK;
+}
+
 int init_chains(bsreg_handle *h, bool refresh_only) {
   const bsreg_options &o = h->opt;
   for (Shard &s : h->shards) {
@@ -900,6 +971,23 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
     delete h; return fail(BSREG_EINVAL, "BSREG_LDET_NODES needs node_re / node_w");
   }
 
+  h->slx_psi = o->slx_psi != 0;
+  if (h->slx_psi) {
+    // connectivity function Psi_SLX(delta) = dist ^ -delta (R/12_slx.R:69-74): SLX model, a handful of lagged columns
+    const int64_t nz = p->nnz_slx > 0 ? p->nnz_slx : p->nnz;
+    const double *dist = p->nnz_slx > 0 ? p->val_slx : p->val;
+    bool ok = true;
+    for (int64_t q = 0; q < nz && ok; ++q) ok = dist[q] > 0.0 && std::isfinite(dist[q]);
+    const char *why = o->model != BSREG_MODEL_LM ? "sampling 'delta' is built for the SLX model (SDM / SDEM: fixed connectivity only)"
+                    : p->k_slx <= 0 || p->k_slx > 8 ? "a connectivity function needs 1 to 8 columns in X_SLX"
+                    : h->m + 2 > 48 ? "too many regressors for a connectivity function (M + 2 <= 48)"
+                    : !ok ? "the values of the Psi_SLX pattern must be positive distances"
+                    : !(o->slx_delta > o->slx_delta_min && o->slx_delta < o->slx_delta_max)
+                        ? "Please provide a valid starting value for delta (spatial) via 'delta'."      // R/41_set_options.R:140
+                    : nullptr;
+    if (why) { delete h; return fail(BSREG_EINVAL, "%s", why); }
+    h->P = h->m + 2;                                              // c(beta, sigma, delta_SLX), R/12_slx.R:117-121
+  }
   if (h->spatial && o->ldet == BSREG_LDET_SPLINE) {
     const int reps = o->ldet_reps > 0 ? o->ldet_reps : 1;
     if (o->ldet_grid_len < 2 || !(o->ldet_grid_to > o->ldet_grid_from)) {
@@ -983,6 +1071,7 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
   pt.mark("log-det nodes");
   pt.begin("bsreg_create: chain init");
   if (rc == BSREG_OK) rc = init_chains(h, false);
+  if (rc == BSREG_OK && h->slx_psi) rc = init_delta(h, o);
   pt.mark("chain init");
   cudaSetDevice(cur);
   if (rc != BSREG_OK) { std::string keep = g_err; bsreg_destroy(h); g_err = keep; return rc; }
@@ -1133,12 +1222,15 @@ int bsreg_get_state(bsreg_handle *h, double *params, double *p0, double *aux, do
     CU(cudaMemcpy(lam.data(), s.cs.lam, (size_t)C * 8, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(ax.data(), s.cs.aux, ax.size() * 8, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(sc.data(), s.cs.mh_scale, sc.size() * 8, cudaMemcpyDeviceToHost));
+    std::vector<double> dl_delta(C, 0.0);
+    if (h->slx_psi) CU(cudaMemcpy(dl_delta.data(), s.dl.delta, (size_t)C * 8, cudaMemcpyDeviceToHost));
     for (int c = 0; c < C; ++c) {
       if (params) {
         double *dst = params + (size_t)(lo + c) * P;
         std::copy(beta.begin() + (size_t)c * m, beta.begin() + (size_t)(c + 1) * m, dst);
         dst[m] = s2[c];
         if (h->spatial) dst[m + 1] = lam[c];
+        if (h->slx_psi) dst[m + 1] = dl_delta[c];
       }
       if (aux) std::copy(ax.begin() + (size_t)c * A, ax.begin() + (size_t)(c + 1) * A, aux + (size_t)(lo + c) * A);
       if (mh_value) { mh_value[2 * (lo + c)] = lam[c]; mh_value[2 * (lo + c) + 1] = ax[(size_t)c * A + 2 * m + 1]; }
@@ -1183,6 +1275,48 @@ int bsreg_set_state(bsreg_handle *h, const double *params, const double *p0, con
   }
   cudaSetDevice(cur);
   return init_chains(h, true);    // recompute the cached log-det / rss at the restored lambda
+}
+
+int bsreg_get_delta_state(bsreg_handle *h, double *delta, double *scale, int64_t *counters) {
+  if (!h) return fail(BSREG_EINVAL, "null handle");
+  if (!h->slx_psi) return fail(BSREG_EINVAL, "the handle has no connectivity function (slx_psi)");
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (Shard &s : h->shards) {
+    CU(cudaSetDevice(s.dev));
+    CU(cudaStreamSynchronize(s.stream));
+    const int C = s.cs.n_chains, lo = s.chain_lo;
+    if (delta) CU(cudaMemcpy(delta + lo, s.dl.delta, (size_t)C * 8, cudaMemcpyDeviceToHost));
+    if (scale) CU(cudaMemcpy(scale + lo, s.dl.scale, (size_t)C * 8, cudaMemcpyDeviceToHost));
+    if (counters) CU(cudaMemcpy(counters + (size_t)lo * 4, s.dl.cnt, (size_t)C * 4 * 8, cudaMemcpyDeviceToHost));
+  }
+  cudaSetDevice(cur);
+  return BSREG_OK;
+}
+
+// Restores value, scale and counters; the chains' Gram matrices are rebuilt at the restored values by one per-chain sweep.
+int bsreg_set_delta_state(bsreg_handle *h, const double *delta, const double *scale, const int64_t *counters) {
+  if (!h) return fail(BSREG_EINVAL, "null handle");
+  if (!h->slx_psi) return fail(BSREG_EINVAL, "the handle has no connectivity function (slx_psi)");
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (Shard &s : h->shards) {
+    CU(cudaSetDevice(s.dev));
+    CU(cudaStreamSynchronize(s.stream));
+    const int C = s.cs.n_chains, lo = s.chain_lo, L = s.dl.L;
+    if (scale) CU(cudaMemcpy(s.dl.scale, scale + lo, (size_t)C * 8, cudaMemcpyHostToDevice));
+    if (counters) CU(cudaMemcpy(s.dl.cnt, counters + (size_t)lo * 4, (size_t)C * 4 * 8, cudaMemcpyHostToDevice));
+    if (delta) {
+      CU(cudaMemcpy(s.dl.delta, delta + lo, (size_t)C * 8, cudaMemcpyHostToDevice));
+      launch_sweep_delta(s.dl, s.dd.X, s.dd.y, h->n, h->m, h->m - L, C, s.dl.delta, s.dl_partial, s.sm_count, s.stream);
+      launch_delta_decide(s.dd, s.dl, h->pr, s.cs, s.ctl_dev, s.draws_dev, s.dl_partial, delta_sweep_ctas(s.sm_count), 1, s.stream);
+      h->launches += 2;
+      CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(s.stream));
+    }
+  }
+  cudaSetDevice(cur);
+  return BSREG_OK;
 }
 
 // ---- parity entry points (shard 0) ----

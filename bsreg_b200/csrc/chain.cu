@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
       if (sar || sem) mh_tune(scale_l, cnt[0], ctl);
       if (sng && pr.sng_theta_scale > 0.0) mh_tune(scale_t, cnt[1], ctl);
     }
-    if (step > ctl.n_burn && ctl.store) {
+    if (step > ctl.n_burn && ctl.store && dd.Gchain == nullptr) {   // sampled delta: delta_decide_kernel stores the draw
       const int row = step - ctl.n_burn - 1 - ctl.save_base;
       if (row >= 0 && row < ctl.save_cap) {
         const int P = m + 1 + ((sar || sem) ? 1 : 0);
@@ -545,7 +545,7 @@ extern "C" int bsreg_debug_trace(long long *out) { return (int)cudaMemcpyFromSym
 #endif
 
 bool chain_fast_supported(const DeviceData &dd, const Priors &pr) {
-  return pr.prior == 0 && dd.m <= FAST_MAX_M && g_staged(dd.m, dd.model);
+  return pr.prior == 0 && dd.m <= FAST_MAX_M && g_staged(dd.m, dd.model) && dd.Gchain == nullptr;
 }
 
 size_t chain_smem_bytes(int m, int model, int) { return work_doubles(m, model) * sizeof(double); }
@@ -645,12 +645,14 @@ void launch_eval_conditionals(const DeviceData &dd, const Priors &pr, const doub
                               const double *sigma2, const double *lam, const double *p0, const double *v, double *mu1,
                               double *rate1, double *rss, double *logpost, cudaStream_t s) {
   const size_t smem = chain_smem_bytes(dd.m, dd.model, pr.prior);
+  DeviceData dv = dd;
+  dv.Gchain = nullptr;                                    // parity entry point: the shared Gram matrix
   if (chain_threads(dd.m) == 32) {
     if (smem_optin((const void *)eval_cond_kernel<32>, smem) != cudaSuccess) return;
-    eval_cond_kernel<32><<<n_eval, 32, smem, s>>>(dd, pr, mu0, beta, sigma2, lam, p0, v, mu1, rate1, rss, logpost);
+    eval_cond_kernel<32><<<n_eval, 32, smem, s>>>(dv, pr, mu0, beta, sigma2, lam, p0, v, mu1, rate1, rss, logpost);
   } else {
     if (smem_optin((const void *)eval_cond_kernel<128>, smem) != cudaSuccess) return;
-    eval_cond_kernel<128><<<n_eval, 128, smem, s>>>(dd, pr, mu0, beta, sigma2, lam, p0, v, mu1, rate1, rss, logpost);
+    eval_cond_kernel<128><<<n_eval, 128, smem, s>>>(dv, pr, mu0, beta, sigma2, lam, p0, v, mu1, rate1, rss, logpost);
   }
 }
 

@@ -177,6 +177,11 @@ template <int NT>
 __device__ __forceinline__ void stage_gram(const DeviceData &dd, double *Gs) {
   if (Gs == nullptr) return;
   const int d = dd.d;
+  if (dd.Gchain != nullptr) {                             // sampled delta: the chain's own Gram matrix (chain = CTA)
+    const double *gc = dd.Gchain + (size_t)blockIdx.x * d * d;
+    for (int e = threadIdx.x; e < d * d; e += NT) Gs[e] = gc[e];
+    return;
+  }
   for (int e = threadIdx.x; e < d * d; e += NT) Gs[e] = g_load(dd, e / d, e - (e / d) * d);
 }
 

@@ -74,6 +74,21 @@ struct DeviceData {
   // grid + spline log-determinant (R/15_sar.R:79-87): spl = [x | y | b | c | d], spl_n knots each (0: nodes are used)
   int spl_n;
   const double *spl;
+  // sampled SLX connectivity parameter (slxdelta.cu): every chain has its own Gram matrix [C][d][d] (its lag columns
+  // depend on its delta); null otherwise
+  const double *Gchain;
+};
+
+// Sampled connectivity parameter delta of the SLX model (slxdelta.cu): Psi(delta)_ij = dist_ij ^ -delta on a fixed pattern
+struct DeltaData {
+  int L, norm, sampled;         // lagged columns; 1 = rows of Psi(delta) divided by their sum; 0 = delta stays at its start
+  const int *rp, *ci;           // pattern (CSR)
+  const double *logd;           // log distances
+  const double *Xl;             // X_SLX row-major [n][L]
+  double *delta, *delta_prop, *scale;   // [C]
+  long long *cnt;               // [C][4] accepted, proposed, accepted_tune, proposed_tune
+  double *Gchain;               // [C][d][d]
+  double prior_a, prior_b, lo, hi;
 };
 
 // entry (i, j) of the Gram matrix from the fixed-point buffer of this launch
@@ -155,6 +170,15 @@ void launch_spmm_dot(int n, const int *rp, const int *ci, const double *va, cons
 void launch_grid_logdets(int size, const int *rp, const int *ci, const double *va, int n_grid, const double *xs_dev,
                          double *A, double reps, double *out, cudaStream_t s);
 void fmm_spline_coefficients(int n, const double *x, const double *y, double *b, double *c, double *d);
+
+// launchers (slxdelta.cu)
+void launch_slx_power_lag(const DeltaData &dl, double delta, double *X, int m, int k_base, int n, cudaStream_t s);
+int  delta_sweep_ctas(int sm_count);
+void launch_sweep_delta(const DeltaData &dl, const double *X, const double *y, int n, int m, int k_base, int n_chains,
+                        const double *delta, double *partial, int sm_count, cudaStream_t s);
+void launch_delta_propose(const DeltaData &dl, const ChainState &cs, cudaStream_t s);
+void launch_delta_decide(const DeviceData &dd, const DeltaData &dl, const Priors &pr, const ChainState &cs, const RunCtl *ctl,
+                         double *draws, const double *partial, int n_parts, int mode, cudaStream_t s);
 
 // launchers (chain.cu)
 size_t chain_smem_bytes(int m, int model, int prior);

@@ -13,7 +13,7 @@ enum Slot : uint32_t {
   SLOT_SIGMA = 0, SLOT_BETA = 1, SLOT_LAMBDA_PROP = 2, SLOT_LAMBDA_ACC = 3,
   SLOT_HS_LAMBDA = 4, SLOT_HS_TAU = 5, SLOT_HS_NU = 6, SLOT_HS_ZETA = 7,
   SLOT_SNG_LAMBDA = 8, SLOT_SNG_TAU = 9, SLOT_SNG_THETA_PROP = 10, SLOT_SNG_THETA_ACC = 11,
-  SLOT_RHO_PROP = 12, SLOT_RHO_ACC = 13, SLOT_PROBE = 64
+  SLOT_RHO_PROP = 12, SLOT_RHO_ACC = 13, SLOT_DELTA_PROP = 14, SLOT_DELTA_ACC = 15, SLOT_PROBE = 64
 };
 
 constexpr int RNG_MAX_CALLS = 1024;

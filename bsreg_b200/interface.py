@@ -290,6 +290,42 @@ class MHView:
         return cnt[2] / max(cnt[3], 1)
 
 
+class DeltaMHView(MHView):
+    """MH object SLX_delta (R/12_slx.R:41-46): same get_* bindings, state kept per chain on the device."""
+
+    def __init__(self, model):
+        self._m, self.name = model, "SLX_delta"
+
+    def _st(self):
+        d = self._m.handle.get_delta_state()
+        return dict(mh_value=d["delta"][:, None], mh_scale=d["scale"][:, None], mh_counters=d["counters"][:, None, :])
+
+    _k = 0
+
+
+class PsiPower:
+    """Connectivity function `Psi(delta) = dist ^ -delta` on the sparsity pattern of `dist` (a sparse matrix of positive
+    distances), rows divided by their sum if normalise = "row": what `Psi_SLX` may be besides a fixed matrix
+    (R/12_slx.R:69-74 takes any closure; this is the paper's inverse-distance family, paper/0_data.R:31-35)."""
+
+    def __init__(self, dist, normalise="row"):
+        self.dist = sp.csr_matrix(dist, dtype=np.float64)
+        self.dist.sort_indices()
+        if normalise not in ("row", "none"):
+            raise ValueError("normalise should be one of 'row', 'none'")
+        if self.dist.nnz and not np.all(self.dist.data > 0):
+            raise ValueError("distances must be positive")
+        self.normalise = normalise
+
+    def __call__(self, delta):
+        W = sp.csr_matrix((np.power(self.dist.data, -float(delta)), self.dist.indices, self.dist.indptr), shape=self.dist.shape)
+        if self.normalise == "row":
+            rs = np.asarray(W.sum(axis=1)).ravel()
+            rs[rs == 0] = 1.0
+            W = sp.diags(1.0 / rs) @ W
+        return sp.csr_matrix(W)
+
+
 @dataclass
 class Model:
     """The object stored as `bm$model`; continuing a fit (`bm.bm`, R/60_interface.R:71-78) reuses it."""
@@ -440,11 +476,28 @@ def get_model(type, y, X, options=None, Psi=None, X_SLX=None, Psi_SLX=None, ldet
     n = len(y)
     has_slx = type in ("slx", "sdm", "sdem")
     spatial = "SAR" if type in ("sar", "sdm") else ("SEM" if type in ("sem", "sdem") else None)
-    if pri["SLX"]["delta_scale"] > 0 or (spatial and pri[spatial]["delta_scale"] > 0):
-        raise NotImplementedError("sampling the connectivity parameter delta (R/12_slx.R:87-106, R/20_mh.R:229-278) "
-                                  "is not built yet; W must be fixed (delta_scale = 0)")
     W = W_slx = None
     kw = {}
+    psi_fun = None                                                      # Psi_SLX given as a connectivity FUNCTION of delta
+    if has_slx:
+        cand = Psi_SLX if Psi_SLX is not None else Psi
+        if isinstance(cand, PsiPower):
+            if type != "slx":
+                raise NotImplementedError("a connectivity function Psi(delta) is built for the SLX model; SDM / SDEM take a "
+                                          "fixed connectivity matrix (R/12_slx.R:87-106 is model-agnostic in the reference)")
+            psi_fun, Psi_SLX, Psi = cand, cand.dist, (cand.dist if Psi_SLX is None else Psi)
+            sl = pri["SLX"]
+            kw["slx_psi"] = dict(normalise=cand.normalise, delta=sl["delta"], delta_scale=sl["delta_scale"],
+                                 delta_a=sl["delta_a"], delta_b=sl["delta_b"], delta_min=sl["delta_min"],
+                                 delta_max=sl["delta_max"])
+        elif callable(cand):
+            raise NotImplementedError("arbitrary connectivity closures cannot cross the C ABI: use PsiPower(dist) "
+                                      "(W(delta) = dist ^ -delta, the paper's family, paper/0_data.R:31-35)")
+    if (psi_fun is None and pri["SLX"]["delta_scale"] > 0 and has_slx):
+        raise ValueError("Connectivity function 'Psi' (SLX) required to sample 'delta'.")           # R/12_slx.R:79
+    if spatial and pri[spatial]["delta_scale"] > 0:
+        raise NotImplementedError("sampling a connectivity parameter of Psi_SAR / Psi_SEM: the reference itself keeps "
+                                  "these fixed (Psi_fixed <- TRUE, R/15_sar.R:54, R/15_sem.R:60)")
     if spatial:
         W = _as_csr(Psi, n, f"Psi_{spatial}")
         ld = (ldet_SAR if spatial == "SAR" else ldet_SEM)
@@ -484,6 +537,8 @@ def get_model(type, y, X, options=None, Psi=None, X_SLX=None, Psi_SLX=None, ldet
         if spatial else None, **kw)
     m = h.m
     names = (["beta"] if m == 1 else [f"beta{i + 1}" for i in range(m)]) + ["sigma"]     # unlist() naming
+    if psi_fun is not None:
+        names.append("delta_SLX")                                       # R/12_slx.R:117-121
     if spatial:
         names.append(f"lambda_{spatial}")
     mdl = Model(h, type, options["type"], names, int(n_chains))
@@ -491,6 +546,8 @@ def get_model(type, y, X, options=None, Psi=None, X_SLX=None, Psi_SLX=None, ldet
         mdl.MH[f"{spatial}_lambda"] = MHView(mdl, 0, f"{spatial}_lambda")
     if options["type"] == "Shrinkage" and sng["theta_scale"] > 0:
         mdl.MH["SNG_theta"] = MHView(mdl, 1, "SNG_theta")
+    if psi_fun is not None and pri["SLX"]["delta_scale"] > 0:
+        mdl.MH["SLX_delta"] = DeltaMHView(mdl)
     return mdl
 
 

@@ -92,6 +92,13 @@ typedef struct {
    * matrices are the leading (n / reps) x (n / reps) block of W (get_W, R/15_sar.R:72-76), at most 4096 wide */
   double ldet_grid_from, ldet_grid_to;
   int32_t ldet_grid_len, ldet_reps;
+  /* Connectivity FUNCTION Psi_SLX(delta) (R/12_slx.R:69-74; SLX model only): slx_psi = 1 reads the values of the
+   * Psi_SLX pattern (val_slx, or val if nnz_slx = 0) as distances d_ij > 0 and uses W(delta)_ij = d_ij ^ -delta
+   * (the paper's inverse-distance decay, paper/0_data.R:31-35), rows divided by their sum if slx_psi_norm = 1.
+   * set_SLX delta part (R/41_set_options.R:115-152): delta is sampled by random-walk MH iff slx_delta_scale > 0
+   * (MH_SLX_delta, R/20_mh.R:229-278); the draws then carry a delta_SLX column after sigma (R/12_slx.R:117-121). */
+  int32_t slx_psi, slx_psi_norm;
+  double slx_delta, slx_delta_scale, slx_delta_a, slx_delta_b, slx_delta_min, slx_delta_max;
   /* chains: this handle runs global chains [chain_offset, chain_offset + n_chains) */
   int32_t n_chains, chain_offset;
   uint64_t seed;
@@ -136,6 +143,10 @@ int  bsreg_get_state(bsreg_handle *h, double *params, double *p0, double *aux, d
 int  bsreg_set_state(bsreg_handle *h, const double *params, const double *p0, const double *aux,
                      const double *mh_value, const double *mh_scale, const int64_t *mh_counters,
                      const int64_t *iterations);
+
+/* State of the MH object SLX_delta per chain: value, proposal scale, counters (4, C) as above.  Pointers may be NULL. */
+int  bsreg_get_delta_state(bsreg_handle *h, double *delta, double *scale, int64_t *counters);
+int  bsreg_set_delta_state(bsreg_handle *h, const double *delta, const double *scale, const int64_t *counters);
 
 /* ---- parity entry points: each runs the same device code the sampler uses ---- */
 /* K1: out = W * B for a host matrix B (n x m column-major)      [R/15_sar.R:57, R/15_sem.R:63-64] */

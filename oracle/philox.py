@@ -57,6 +57,8 @@ class Slot:
     SNG_THETA_ACC = 11   # 1 uniform        R/20_mh.R:74
     RHO_PROP = 12      # SEM truncated RW   R/20_mh.R:173-177 (MH_SEM_lambda alias :218)
     RHO_ACC = 13       # SEM accept uniform
+    DELTA_PROP = 14    # SLX connectivity parameter, truncated RW   R/20_mh.R:245-250
+    DELTA_ACC = 15     # accept uniform                             R/20_mh.R:74
     PROBE = 64         # Rademacher probes for the trace estimator (setup, iteration = 0)
 
 

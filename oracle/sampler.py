@@ -39,6 +39,8 @@ def default_priors() -> dict:
         SNG=dict(lambda_a=0.01, lambda_b=0.01, theta_scale=0.0, theta_a=1.0, lam=1.0, tau=10.0, theta=0.1),
         HS=dict(lam=1.0, tau=1.0, zeta=1.0, nu=1.0),
         SAR=dict(spatial), SEM=dict(spatial),
+        # set_SLX = set_SAR (R/41_set_options.R:149), delta part: delta_scale = 0 keeps the connectivity fixed
+        SLX=dict(delta_a=1.01, delta_b=1.01, delta=1.0, delta_scale=0.0, delta_min=1e-12, delta_max=float("inf")),
     )
 
 
@@ -163,6 +165,7 @@ class RefChain:
     ldet: dict = field(default_factory=lambda: dict(kind="eigen", reps=1))
     rng: object = None
     dense_sem: bool = False
+    psi_slx: dict = None             # connectivity FUNCTION Psi_SLX(delta) (R/12_slx.R:69-74): see psi_power()
 
     def __post_init__(self):
         assert self.model in MODELS and self.prior_type in PRIORS
@@ -184,11 +187,20 @@ class RefChain:
     def _setup(self):
         if self.W is not None:
             self.W = core.as_csr(self.W)
-        # setup_2SLX, fixed-W branch: R/12_slx.R:51-68
+        # setup_2SLX: R/12_slx.R:51-84 (fixed matrix :60-68; connectivity function + set_delta :69-74, :26-36)
+        self.delta = None
         if self.has_slx:
-            Ws = core.as_csr(self.W_slx) if self.W_slx is not None else self.W
             Xl = np.asarray(self.X_slx, dtype=np.float64).reshape(self.X.shape[0], -1)
-            self.X = np.hstack([self.X, core.spmm(Ws, Xl)])
+            if self.psi_slx is not None:
+                assert self.model == "slx", "sampled delta is restated for the SLX model only"
+                self.X_base, self.X_lag = self.X, Xl
+                self.delta = float(self.priors["SLX"]["delta"])
+                self.X = np.hstack([self.X_base, core.spmm(psi_power(self.psi_slx, self.delta), Xl)])
+                if self.priors["SLX"]["delta_scale"] > 0:                  # R/12_slx.R:41-46
+                    self.MH["delta"] = MHState(self.delta, float(self.priors["SLX"]["delta_scale"]))
+            else:
+                Ws = core.as_csr(self.W_slx) if self.W_slx is not None else self.W
+                self.X = np.hstack([self.X, core.spmm(Ws, Xl)])
         self.N, self.M = self.X.shape
         N, M = self.N, self.M
         # setup_4NG: R/10_lm.R:142-153
@@ -334,19 +346,51 @@ class RefChain:
             self.lam = mh.value
             self._refresh()
 
+    def _sample_delta(self, it):
+        """sample_extra3, R/12_slx.R:87-106 + MH_SLX_delta R/20_mh.R:229-278: random-walk MH on the connectivity
+        parameter; rss(v) re-solves for beta with X(v) = [X, Psi(v) X_SLX] at the current sigma^2 and P0 (:91-97);
+        prior dgamma(1 / v, a, rate = b, log) without a Jacobian (quirk Q7, :269); truncated proposal, no Hastings
+        correction (:245-263)."""
+        mh = self.MH["delta"]
+        sl = self.priors["SLX"]
+        a, b = float(sl["delta_a"]), float(sl["delta_b"])
+
+        def rss(v):
+            X = np.hstack([self.X_base, core.spmm(psi_power(self.psi_slx, v), self.X_lag)])
+            _, beta = core.beta_moments(X.T @ X, X.T @ self.y, self.sigma2, self.p0, self.mu0)
+            return core.sq_sum(self.y - X @ beta)
+
+        def post(v):
+            r = rss(v)
+            if not r > 0.0:
+                return float("nan")
+            x = 1.0 / v
+            return -0.5 * (self.N - self.M) * math.log(r) + (a * math.log(b) - math.lgamma(a) + (a - 1.0) * math.log(x) - b * x)
+        prop = self.rng.truncated_rw(it, Slot.DELTA_PROP, mh.value, mh.scale, float(sl["delta_min"]), float(sl["delta_max"]))
+        prob = _exp(post(prop) - post(mh.value))
+        mh.finalize(self.rng.uniform(it, Slot.DELTA_ACC), prob, prop)
+        if abs(mh.value - self.delta) > 1e-12:                 # set_delta, R/12_slx.R:26-36, :104
+            self.delta = mh.value
+            self.X = np.hstack([self.X_base, core.spmm(psi_power(self.psi_slx, self.delta), self.X_lag)])
+            self._refresh()
+
     def sample(self):
-        """Base$sample, R/10_lm.R:46-63: sigma, beta, shrinkage, latent, volatility, finalize."""
+        """Base$sample, R/10_lm.R:46-63: sigma, beta, shrinkage, latent, volatility, extra1-3, finalize."""
         it = self.iterations + 1
         self._sample_sigma(it)
         self._sample_beta(it)
         self._sample_shrinkage(it)
         if self.has_sar or self.has_sem:
             self._sample_lambda(it)
+        if "delta" in self.MH:
+            self._sample_delta(it)
         self.iterations += 1                               # R/10_lm.R:73-77
 
     # -- R/10_lm.R:193, R/15_sar.R:138-142, R/15_sem.R:142-146 -----------------
     def get_parameters(self) -> np.ndarray:
         out = list(self.beta) + [math.sqrt(self.sigma2)]
+        if self.delta is not None:                         # pars$delta_SLX, R/12_slx.R:117-121
+            out.append(self.delta)
         if self.has_sar or self.has_sem:
             out.append(self.lam)
         return np.array(out)
@@ -354,11 +398,26 @@ class RefChain:
     def parameter_names(self):
         names = ["beta"] if self.M == 1 else [f"beta{i + 1}" for i in range(self.M)]
         names.append("sigma")
+        if self.delta is not None:
+            names.append("delta_SLX")
         if self.has_sar:
             names.append("lambda_SAR")
         if self.has_sem:
             names.append("lambda_SEM")
         return names
+
+
+def psi_power(psi: dict, delta: float) -> sp.csr_matrix:
+    """The connectivity family the C ABI offers for `Psi_SLX(delta)` (the reference takes any R closure; the paper's is
+    inverse-distance decay, paper/0_data.R:31-35): W(delta)_ij = dist_ij ^ -delta on a fixed sparsity pattern,
+    normalise = "row" divides every row by its sum, "none" leaves it."""
+    D = psi["dist"]
+    W = sp.csr_matrix((np.power(D.data, -delta), D.indices, D.indptr), shape=D.shape)
+    if psi.get("normalise", "row") == "row":
+        rs = np.asarray(W.sum(axis=1)).ravel()
+        rs[rs == 0.0] = 1.0
+        W = sp.diags(1.0 / rs) @ W
+    return sp.csr_matrix(W)
 
 
 def _exp(x: float) -> float:

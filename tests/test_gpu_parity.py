@@ -617,3 +617,94 @@ def test_chain_with_grid_spline_logdet_matches_oracle(model):
 
 
 MODEL_CODE_ = {"sar": 1, "sem": 2}
+
+
+# ---------------------------------------------------------------------------
+# sampled connectivity parameter delta of the SLX model (R/12_slx.R:87-106, R/20_mh.R:229-278): csrc/slxdelta.cu
+# ---------------------------------------------------------------------------
+def _delta_problem(n=900, knn=6, seed=0, k=3):
+    import scipy.sparse as sp
+    from bsreg_b200.synthetic import knn_weights
+    from oracle.sampler import psi_power
+    W, pts = knn_weights(n, knn)
+    r = np.repeat(np.arange(n), np.diff(W.indptr))
+    D = sp_csr(sp.csr_matrix((np.linalg.norm(pts[r] - pts[W.indices], axis=1), W.indices, W.indptr), shape=W.shape))
+    rng = np.random.default_rng(seed)
+    X = np.column_stack([np.ones(n), rng.standard_normal((n, k - 1))])
+    Xl = X[:, 1:3].copy()
+    y = X @ rng.standard_normal(k) + psi_power(dict(dist=D, normalise="row"), 3.0) @ Xl @ np.array([0.8, -0.5]) \
+        + 0.3 * rng.standard_normal(n)
+    return y, X, Xl, D
+
+
+@pytest.mark.parametrize("prior,normalise", [("Independent", "row"), ("Horseshoe", "row"), ("Independent", "none")])
+def test_sampled_delta_chain_matches_oracle(prior, normalise):
+    """Every chain proposes its own delta: the per-chain sweep forms W(delta') X_SLX and the Gram blocks it touches, the
+    decision kernel re-solves for beta at the proposal and at the current value.  Trajectories (beta, sigma, delta_SLX)
+    against the oracle, burn-in tuning of the delta proposal scale and continuation included."""
+    from oracle.sampler import PhiloxRNG, RefChain, sample
+    capi = capi_mod()
+    y, X, Xl, D = _delta_problem()
+    slx = dict(delta=2.0, delta_scale=0.3, delta_a=2.0, delta_b=2.0, delta_min=1e-12, delta_max=float("inf"))
+    n_burn, n_save, off = 50, 40, 3
+    with capi.Handle(y, X, model=capi.MODEL_LM, prior=PRIOR_CODE_[prior], W=D, X_slx=Xl, n_chains=5, chain_offset=off, seed=13,
+                     slx_psi=dict(normalise=normalise, **slx)) as h:
+        assert h.P == X.shape[1] + 2 + 2
+        a = h.run(n_burn, 25)
+        b = h.run(0, n_save - 25)
+        got = np.concatenate([a, b], axis=2)
+        st = h.get_delta_state()
+        assert h.get_state()["iterations"].tolist() == [n_burn + n_save] * 5
+    for c in (0, 4):
+        ch = RefChain("slx", y, X, X_slx=Xl, psi_slx=dict(dist=D, normalise=normalise), prior_type=prior,
+                      priors={"SLX": slx}, rng=PhiloxRNG(13, off + c))
+        ref = sample(ch, n_save, n_burn)
+        assert ch.parameter_names()[-1] == "delta_SLX"
+        assert relnorm(got[c].T, ref) < 1e-7, (prior, c)
+        mh = ch.MH["delta"]
+        assert abs(st["scale"][c] - mh.scale) < 1e-12 * mh.scale
+        assert st["counters"][c].tolist() == [mh.accepted, mh.proposed, mh.accepted_tune, mh.proposed_tune]
+        assert abs(st["delta"][c] - mh.value) < 1e-9
+
+
+PRIOR_CODE_ = {"Independent": 0, "Conjugate": 1, "Shrinkage": 2, "Horseshoe": 3}
+
+
+def test_connectivity_function_with_fixed_delta_equals_the_fixed_matrix():
+    """delta_scale = 0 (the default): Psi(delta0) is used as it is -- same beta and sigma draws as the fixed-matrix SLX
+    model with W = Psi(delta0) (to rounding: the lags are formed by another kernel), plus a constant delta_SLX column."""
+    from oracle.sampler import psi_power
+    capi = capi_mod()
+    y, X, Xl, D = _delta_problem(n=700)
+    with capi.Handle(y, X, model=capi.MODEL_LM, W=D, X_slx=Xl, n_chains=2, seed=5,
+                     slx_psi=dict(normalise="row", delta=2.5, delta_scale=0.0)) as h:
+        fun = h.run(20, 30)
+    Wfix = sp_csr(psi_power(dict(dist=D, normalise="row"), 2.5))
+    with capi.Handle(y, X, model=capi.MODEL_LM, W=Wfix, X_slx=Xl, n_chains=2, seed=5) as h:
+        fix = h.run(20, 30)
+    assert np.all(fun[:, -1, :] == 2.5)
+    assert relnorm(fun[:, :-1, :], fix) < 1e-9
+
+
+def test_delta_state_round_trip_and_interface():
+    import bsreg_b200 as bs
+    capi = capi_mod()
+    y, X, Xl, D = _delta_problem(n=600)
+    kw = dict(model=capi.MODEL_LM, W=D, X_slx=Xl, n_chains=3, seed=21,
+              slx_psi=dict(normalise="row", delta=2.0, delta_scale=0.2, delta_a=2.0, delta_b=2.0))
+    with capi.Handle(y, X, **kw) as h:
+        whole = h.run(30, 30)
+    with capi.Handle(y, X, **kw) as h:
+        first = h.run(30, 12)
+        st, dst = h.get_state(), h.get_delta_state()
+    with capi.Handle(y, X, **kw) as h2:                   # a fresh handle continues from the saved state
+        h2.set_state(st)
+        h2.set_delta_state(dst)
+        rest = h2.run(0, 18)
+    assert relnorm(np.concatenate([first, rest], axis=2), whole) < 1e-9
+    # public interface: bslx with a connectivity function, the paper's call (paper/1b_estimate_dist.R:19-22)
+    fit = bs.bslx((y, X), W=bs.PsiPower(D), X_SLX=Xl, n_save=200, n_burn=200, verbose=False, seed=4, n_chains=4,
+                  options=bs.set_options(SLX=bs.set_SLX(delta=3, delta_scale=0.05, delta_a=2, delta_b=2)))
+    assert fit.colnames[-2:] == ["sigma", "delta_SLX"] and fit.chains.shape == (4, 200, X.shape[1] + 2 + 2)
+    assert abs(fit.chains[:, :, -1].mean() - 3.0) < 0.5                  # simulated with delta = 3
+    assert 0.0 < fit.model.MH["SLX_delta"].get_acceptance() < 1.0 and "SLX_delta" in fit.model.get_meta

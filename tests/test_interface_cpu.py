@@ -90,9 +90,12 @@ def test_errors_that_precede_device_work():
         bs.bsar((y, X), W=np.eye(4), verbose=False)
     with pytest.raises(NotImplementedError, match="stochastic volatility"):
         bs.bsv((y, X))
-    with pytest.raises(NotImplementedError, match="delta"):
+    with pytest.raises(ValueError, match=r"Connectivity function 'Psi' \(SLX\) required to sample 'delta'"):   # R/12_slx.R:79
         bs.bslx((y, np.column_stack([np.ones(10), np.arange(10.)])), W=np.eye(10),
                 options=bs.set_options(SLX=bs.set_SLX(delta_scale=0.1)), verbose=False)
+    with pytest.raises(NotImplementedError, match="SLX model"):
+        bs.bsdm((y, np.column_stack([np.ones(10), np.arange(10.)])), W=bs.PsiPower(np.ones((10, 10)) - np.eye(10)), verbose=False)
+    assert np.allclose(bs.PsiPower(np.array([[0, 2.0], [4.0, 0]]), "none")(2).toarray(), [[0, 0.25], [1 / 16, 0]])
     with pytest.raises(ValueError, match="should be one of"):
         bs.bm((y, X), type="probit")
     with pytest.raises(ValueError, match="'reps' must divide"):
