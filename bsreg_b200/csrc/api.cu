@@ -48,7 +48,8 @@ struct PhaseTimer {
   void mark(const char *what) {
     if (open) { nvtxRangePop(); open = false; }
     if (!on) return;
-    cudaDeviceSynchronize();
+    static const bool host_only = getenv("BSREG_TIMING") && atoi(getenv("BSREG_TIMING")) == 2;   // 2: no device sync
+    if (!host_only) cudaDeviceSynchronize();
     const auto now = std::chrono::steady_clock::now();
     fprintf(stderr, "[bsreg timing] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
     t = now;
@@ -148,6 +149,25 @@ struct PoolTmp {
   template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
+// Small pinned host blocks (results of the trace moments): cudaMallocHost / cudaFreeHost cost hundreds of microseconds
+// and synchronise the device, so blocks are recycled across fits like the device buffers above.
+std::vector<void *> g_pinned_free;
+constexpr size_t PINNED_BLOCK = 4096;
+
+cudaError_t pinned_get(void **p) {
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_pinned_free.empty()) { *p = g_pinned_free.back(); g_pinned_free.pop_back(); return cudaSuccess; }
+  }
+  return cudaMallocHost(p, PINNED_BLOCK);
+}
+
+void pinned_put(void *p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_pinned_free.push_back(p);
+}
+
 constexpr int GRAPH_UNROLL = 24;      // Gibbs iterations per CUDA graph launch (multiple of the 3 Gram buffers)
 constexpr int BLOCK_ITERS = 1000;     // iterations between host syncs / progress callbacks
 constexpr size_t DRAW_BUF_BYTES = (size_t)1 << 30;
@@ -195,6 +215,8 @@ struct bsreg_handle {
   int64_t nnz = 0;
   std::vector<double> node_re, node_im, node_w;
   std::vector<double> spline;         // BSREG_LDET_SPLINE: [x | y | b | c | d]
+  bool have_trace_w = false;
+  double trace_w = 0.0;               // tr(W), from the validation pass over the CSR
 };
 
 namespace {
@@ -364,6 +386,7 @@ struct MomentsJob {
   int order = 0, probes = 0;
   double m1 = 0.0;
   double *U = nullptr, *buf[3] = {nullptr, nullptr, nullptr}, *res = nullptr, *rowsum = nullptr, *scratch = nullptr;
+  double *partial = nullptr;          // tiles mode: one row of per-CTA dot partials per order
   double *host = nullptr;             // pinned: res[0 .. order], then tr(W^2) partial at [order + 1]
   cudaEvent_t done = nullptr;
 };
@@ -373,7 +396,8 @@ int trace_moments_launch(bsreg_handle *h, Shard &s, const bsreg_problem *prob_cs
   const int n = h->n;
   job.order = order; job.probes = probes; job.active = true;
   CU(cudaSetDevice(s.dev));
-  CU(cudaMallocHost((void **)&job.host, (size_t)(order + 2) * 8));
+  if ((size_t)(order + 2) * 8 > PINNED_BLOCK) return fail(BSREG_EINVAL, "Chebyshev order too large");
+  CU(pinned_get((void **)&job.host));
   for (int j = 0; j <= order + 1; ++j) job.host[j] = 0.0;
   CU(cudaEventCreateWithFlags(&job.done, cudaEventDisableTiming));
   CU(pool_malloc((void **)&job.res, (size_t)(order + 2) * 8));
@@ -388,6 +412,8 @@ int trace_moments_launch(bsreg_handle *h, Shard &s, const bsreg_problem *prob_cs
     const size_t len = (size_t)n * probes;
     CU(pool_malloc((void **)&job.U, len * 8));
     for (int b = 0; b < 3; ++b) CU(pool_malloc((void **)&job.buf[b], len * 8));
+    const int parts = spmm_dot_parts(n, probes);
+    CU(pool_malloc((void **)&job.partial, (size_t)(order + 1) * parts * 8));
     launch_probes(job.U, n, probes, seed, st);
     // T_1 = W U ; T_j = 2 W T_{j-1} - T_{j-2}; U stays intact for the dots u'T_j u
     launch_spmm(n, s.dd.rp, s.dd.ci, s.dd.va, job.U, probes, probes, job.buf[0], probes, 0, 1.0, nullptr, 0.0, st);
@@ -398,24 +424,32 @@ int trace_moments_launch(bsreg_handle *h, Shard &s, const bsreg_problem *prob_cs
     for (int j = 2; j <= order; ++j) {
       double *next = job.buf[nxt];
       if (j >= 3) {          // the dot u'T_j u rides on the product
-        launch_spmm_dot(n, s.dd.rp, s.dd.ci, s.dd.va, cur, probes, next, 2.0, prev, -1.0, job.U, job.scratch, job.res + j, st);
-        h->launches += 2;
+        launch_spmm_dot(n, s.dd.rp, s.dd.ci, s.dd.va, cur, probes, next, 2.0, prev, -1.0, job.U,
+                        job.partial + (size_t)j * parts, nullptr, st);
+        ++h->launches;
       } else {
         launch_spmm(n, s.dd.rp, s.dd.ci, s.dd.va, cur, probes, probes, next, probes, 0, 2.0, prev, -1.0, st);
         ++h->launches;
       }
       prev = cur; cur = next; nxt = (nxt + 1) % 3;
     }
+    // the dots of all orders in one launch (one warp per order, fixed order) instead of one small launch per order
+    launch_combine_rows(job.partial + (size_t)3 * parts, parts, order - 2, job.res + 3, st);
+    ++h->launches;
   }
   CU(cudaMemcpyAsync(job.host, job.res, (size_t)(order + 2) * 8, cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(job.done, st));
-  // tr(W) on the host while the device works
+  // tr(W): summed during the validation pass of bsreg_create; here only for the parity entry point
   if (order >= 1) {
-    long double tr = 0.0L;
-    for (int i = 0; i < n; ++i)
-      for (int p = prob_csr->row_ptr[i]; p < prob_csr->row_ptr[i + 1]; ++p)
-        if (prob_csr->col_idx[p] == i) tr += prob_csr->val[p];
-    job.m1 = (double)tr;
+    if (h->have_trace_w) {
+      job.m1 = h->trace_w;
+    } else {
+      long double tr = 0.0L;
+      for (int i = 0; i < n; ++i)
+        for (int p = prob_csr->row_ptr[i]; p < prob_csr->row_ptr[i + 1]; ++p)
+          if (prob_csr->col_idx[p] == i) tr += prob_csr->val[p];
+      job.m1 = (double)tr;
+    }
   }
   return BSREG_OK;
 }
@@ -434,7 +468,8 @@ int trace_moments_finish(bsreg_handle *h, Shard &s, MomentsJob &job, double *mom
   for (int b = 0; b < 3; ++b) if (job.buf[b]) pool_free(job.buf[b]);
   if (job.rowsum) pool_free(job.rowsum);
   pool_free(job.res); pool_free(job.scratch);
-  cudaFreeHost(job.host);
+  if (job.partial) pool_free(job.partial);
+  pinned_put(job.host);
   cudaEventDestroy(job.done);
   job = MomentsJob();
   return BSREG_OK;
@@ -498,10 +533,13 @@ static void bfs_order(int n, const int *rp, const int *ci, std::vector<int> &per
     if (seen[root]) continue;
     seen[root] = 1; perm[tail++] = root;
     while (head < tail) {
+      // the queue is the prefetch list: row pointers 8 vertices ahead, their column lists 4 ahead
+      if (head + 8 < tail) __builtin_prefetch(rp + perm[head + 8]);
+      if (head + 4 < tail) __builtin_prefetch(ci + rp[perm[head + 4]]);
       const int v = perm[head++];
       for (int q = rp[v]; q < rp[v + 1]; ++q) {
-        const int u = ci[q];
-        if (!seen[u]) { seen[u] = 1; perm[tail++] = u; }
+        const unsigned u = (unsigned)ci[q];
+        if (u < (unsigned)n && !seen[u]) { seen[u] = 1; perm[tail++] = (int)u; }   // (a bad index is reported by the validation pass)
       }
     }
   }
@@ -511,6 +549,16 @@ static void bfs_order(int n, const int *rp, const int *ci, std::vector<int> &per
 struct SharedOrder {
   std::once_flag once;
   std::vector<int> perm;
+  std::thread worker;                 // started by bsreg_create before the validation pass and the uploads
+  ~SharedOrder() { if (worker.joinable()) worker.join(); }
+  void start(bool wanted, int n, const int *rp, const int *ci) {
+    if (!wanted) return;
+    worker = std::thread([this, n, rp, ci] { if (wants_reorder(n, rp, ci)) bfs_order(n, rp, ci, perm); });
+  }
+  const std::vector<int> &get() {
+    std::call_once(once, [this] { if (worker.joinable()) worker.join(); });
+    return perm;
+  }
 };
 
 int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_options *o, int n_chains, int chain_lo,
@@ -603,11 +651,9 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   }
   // internal ordering of the observations for the tiled sweep (the Gram matrix does not depend on it): breadth-first when
   // W has no locality.  Host work, done here so that it runs beside the uploads and transposes enqueued above.
-  std::call_once(order.once, [&] {
-    if (h->model != BSREG_MODEL_LM && d <= 88 && p->nnz > 0 && wants_reorder(n, p->row_ptr, p->col_idx))
-      bfs_order(n, p->row_ptr, p->col_idx, order.perm);
-  });
-  const std::vector<int> &perm = order.perm;
+  pt.mark("y, X enqueue");
+  const std::vector<int> &perm = order.get();
+  pt.mark("host ordering (BFS)");
   tmp.release();                                             // drains the stream first
   dd.y = y; dd.X = X;
   h->launches += 1;
@@ -761,14 +807,17 @@ int setup_shard(bsreg_handle *h, Shard &s, const bsreg_problem *p, const bsreg_o
   // ---- Gram accumulators and fixed-point scales ----
   double *norms, *gscale, *ginv;
   TRY(s.alloc(&dd.Gfix, (size_t)3 * d * d));
-  TRY(s.alloc(&norms, (size_t)d)); TRY(s.alloc(&gscale, (size_t)d * d)); TRY(s.alloc(&ginv, (size_t)d * d));
+  const int nparts = colnorm_parts();
+  TRY(s.alloc(&norms, (size_t)nparts * d)); TRY(s.alloc(&gscale, (size_t)d * d)); TRY(s.alloc(&ginv, (size_t)d * d));
   TRY(s.alloc(&s.scratch, 4096));
   CU(cudaMemsetAsync(dd.Gfix, 0, (size_t)3 * d * d * 8, s.stream));
   launch_colnorms(dd, norms, s.stream);
   ++h->launches;
-  std::vector<double> hn(d), hs((size_t)d * d), hi((size_t)d * d);
-  CU(cudaMemcpyAsync(hn.data(), norms, (size_t)d * 8, cudaMemcpyDeviceToHost, s.stream));
+  std::vector<double> hn(d, 0.0), hpart((size_t)nparts * d), hs((size_t)d * d), hi((size_t)d * d);
+  CU(cudaMemcpyAsync(hpart.data(), norms, (size_t)nparts * d * 8, cudaMemcpyDeviceToHost, s.stream));
   CU(cudaStreamSynchronize(s.stream));
+  for (int b = 0; b < nparts; ++b)
+    for (int i = 0; i < d; ++i) hn[i] += hpart[(size_t)b * d + i];
   for (int i = 0; i < d; ++i)
     for (int j = 0; j < d; ++j) {
       const double bound = std::sqrt(hn[i] * hn[j]);
@@ -922,15 +971,24 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
   const bool need_w = o->model != BSREG_MODEL_LM || p->k_slx > 0;
   if (need_w && (!p->row_ptr || !p->col_idx || !p->val || p->nnz <= 0))
     return fail(BSREG_EINVAL, "Please provide a connectivity matrix (CSR row_ptr/col_idx/val)");   // R/15_sar.R:52
+  SharedOrder order;
+  long double trace_w = 0.0L;
   if (need_w) {
     if (p->row_ptr[0] != 0 || p->row_ptr[p->n] != p->nnz) return fail(BSREG_EINVAL, "CSR row_ptr inconsistent with nnz");
-    // one pass: index range, and max_i sum_j |W_ij| for the Chebyshev log-determinant below
+    for (int i = 0; i < p->n; ++i)
+      if (p->row_ptr[i + 1] < p->row_ptr[i]) return fail(BSREG_EINVAL, "CSR row_ptr must be non-decreasing");
+    // the internal ordering of the observations (breadth-first relabelling when W has no locality: ~3 ms of host work at
+    // N = 1e5) is computed by a helper thread beside the validation pass, the uploads and the trace moments
+    const int d_gram = (o->model == BSREG_MODEL_SEM ? 2 : 1) * (p->k + p->k_slx) + 2;
+    order.start(o->model != BSREG_MODEL_LM && d_gram <= 88 && p->nnz > 0, p->n, p->row_ptr, p->col_idx);
+    // one pass: index range, max_i sum_j |W_ij| for the Chebyshev log-determinant below, and tr(W)
     double row_norm = 0.0;
     for (int i = 0; i < p->n; ++i) {
       double rs = 0.0;
       for (int64_t q = p->row_ptr[i]; q < p->row_ptr[i + 1]; ++q) {
         if (p->col_idx[q] < 0 || p->col_idx[q] >= p->n) return fail(BSREG_EINVAL, "CSR column index out of range");
         rs += std::fabs(p->val[q]);
+        if (p->col_idx[q] == i) trace_w += p->val[q];
       }
       row_norm = std::max(row_norm, rs);
     }
@@ -954,6 +1012,7 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
     return fail(BSREG_ENOGPU, "no CUDA device available (this library has no CPU fallback)");
   }
 
+  pt0.mark("argument validation");
   PhaseTimer pt;
   bsreg_handle *h = new bsreg_handle();
   h->n = p->n; h->k = p->k; h->m = p->k + p->k_slx; h->model = o->model; h->prior = o->prior;
@@ -1018,7 +1077,7 @@ int bsreg_create(const bsreg_problem *p, const bsreg_options *o, bsreg_handle **
   h->shards.resize(ndev);
   int rc = BSREG_OK, lo = 0;
   MomentsJob mjob;
-  SharedOrder order;
+  h->have_trace_w = need_w; h->trace_w = (double)trace_w;
   const bool want_moments = h->spatial && o->ldet == BSREG_LDET_CHEBYSHEV;
   std::vector<int> cnts(ndev), los(ndev);
   for (int g = 0; g < ndev && rc == BSREG_OK; ++g) {
@@ -1519,6 +1578,9 @@ void bsreg_release_cache(void) {
   int cur = 0;
   cudaGetDevice(&cur);
   for (const FreeBlock &b : drop) { cudaSetDevice(b.dev); cudaFree(b.ptr); }
+  std::vector<void *> pins;
+  { std::lock_guard<std::mutex> lk(g_pool_mu); pins.swap(g_pinned_free); }
+  for (void *q : pins) cudaFreeHost(q);
   cudaSetDevice(cur);
 }
 

@@ -136,7 +136,8 @@ cudaError_t smem_optin(const void *kernel, size_t bytes);
 void launch_transpose(const double *src_colmajor, double *dst_rowmajor, int n, int m, int ld_dst, int col0, cudaStream_t s);
 void launch_spmm(int n, const int *rp, const int *ci, const double *va, const double *B, int m, int ldb,
                  double *out, int ldo, int col0, double alpha, const double *C, double beta, cudaStream_t s);
-void launch_colnorms(const DeviceData &dd, double *norms, cudaStream_t s);
+int  colnorm_parts();
+void launch_colnorms(const DeviceData &dd, double *partial, cudaStream_t s);   // partial: colnorm_parts() * d
 bool sweep_fast_supported(const DeviceData &dd);
 bool sweep_ring_supported(int d, int model, int max_blob, int max_nu);   // does the TMA-fed ring sweep cover this design
 void launch_pack_tiles(const double *X, const double *y, const int *perm, double *Zt, double *yp, int n, int m, cudaStream_t s);
@@ -161,7 +162,9 @@ void launch_sweep(const DeviceData &dd, int sm_count, cudaStream_t s);
 int  sweep_launch_count();
 void launch_residual_ss(const DeviceData &dd, int n_eval, const double *beta,
                         const double *lam, const double *rho, double *partial, double *out, cudaStream_t s);
-void launch_probes(double *U, int n, int n_probes, uint64_t seed, cudaStream_t s);
+void launch_probes(double *U, int n, int n_probes, uint64_t seed, cudaStream_t s, const int *perm = nullptr, int n_rows = 0);
+int  spmm_dot_parts(int n, int m);   // per-CTA partials launch_spmm_dot writes
+void launch_combine_rows(const double *partial, int nparts, int count, double *out, cudaStream_t s);
 void launch_dot(const double *a, const double *b, int64_t len, double *partial, double *out, cudaStream_t s);
 void launch_spmm_dot(int n, const int *rp, const int *ci, const double *va, const double *B, int m, double *out, double alpha,
                      const double *C, double beta, const double *U, double *partial, double *dot, cudaStream_t s);

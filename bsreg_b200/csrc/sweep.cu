@@ -356,7 +356,28 @@ void launch_spmm_dot(int n, const int *rp, const int *ci, const double *va, cons
   int grid = (int)((total + block - 1) / block < 148 * 16 ? (total + block - 1) / block : 148 * 16);
   if (grid < 1) grid = 1;
   csr_spmm_kernel<true><<<grid, block, 0, s>>>(n, rp, ci, va, B, m, m, out, m, 0, alpha, C, beta, U, partial);
-  combine_partials_kernel<<<1, 32, 0, s>>>(partial, grid, 1, 1, dot);
+  if (dot != nullptr) combine_partials_kernel<<<1, 32, 0, s>>>(partial, grid, 1, 1, dot);   // null: the caller combines all orders at once
+}
+
+int spmm_dot_parts(int n, int m) {
+  const size_t total = (size_t)n * m;
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  return grid < 1 ? 1 : grid;
+}
+
+// out[e] = sum of row e of partial [count][nparts] (one warp per entry, fixed order): all orders of the recurrence at once
+__global__ void combine_rows_kernel(const double *partial, int nparts, int count, double *out) {
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (e >= count) return;
+  double s0 = 0.0;
+  for (int b = lane; b < nparts; b += 32) s0 += partial[(size_t)e * nparts + b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+  if (lane == 0) out[e] = s0;
+}
+
+void launch_combine_rows(const double *partial, int nparts, int count, double *out, cudaStream_t s) {
+  combine_rows_kernel<<<(count + 7) / 8, 256, 0, s>>>(partial, nparts, count, out);
 }
 
 // ---------------------------------------------------------------------------
@@ -369,25 +390,33 @@ __device__ __forceinline__ double z_entry(const DeviceData &dd, int row, int c) 
   return dd.WX[(size_t)row * dd.m + c - 2 - dd.m];
 }
 
-__global__ void colnorm_kernel(DeviceData dd, double *norms) {
-  __shared__ double red[256];
-  const int c = blockIdx.x;
-  double acc = 0.0;
-  for (int row = threadIdx.x; row < dd.n; row += blockDim.x) {
-    const double v = z_entry(dd, row, c);
-    acc = fma(v, v, acc);
-  }
-  red[threadIdx.x] = acc;
+// One warp per row reads the row's y, Wy, X (and WX) entries with coalesced loads; per-CTA column sums in shared memory
+// (fixed order inside the CTA), partial[cta][d]; the host adds the COLNORM_CTAS partials in order (the norms only fix
+// power-of-two scales, but a run-to-run difference in one of them would change the rounding of the fixed-point Gram).
+constexpr int COLNORM_CTAS = 296, COLNORM_MAXD = 512;
+__global__ void __launch_bounds__(256) colnorm_kernel(DeviceData dd, double *partial) {
+  __shared__ double acc[8][COLNORM_MAXD];
+  const int d = dd.d, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int c = lane; c < d; c += 32) acc[wid][c] = 0.0;
+  __syncwarp();
+  for (int row = blockIdx.x * 8 + wid; row < dd.n; row += gridDim.x * 8)
+    for (int c = lane; c < d; c += 32) {
+      const double v = z_entry(dd, row, c);
+      acc[wid][c] = fma(v, v, acc[wid][c]);
+    }
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
+  for (int c = threadIdx.x; c < d; c += 256) {
+    double s0 = 0.0;
+    for (int w = 0; w < 8; ++w) s0 += acc[w][c];
+    partial[(size_t)blockIdx.x * d + c] = s0;
   }
-  if (threadIdx.x == 0) norms[c] = red[0];
 }
 
-void launch_colnorms(const DeviceData &dd, double *norms, cudaStream_t s) {
-  colnorm_kernel<<<dd.d, 256, 0, s>>>(dd, norms);
+int colnorm_parts() { return COLNORM_CTAS; }
+
+// partial: colnorm_parts() * d doubles
+void launch_colnorms(const DeviceData &dd, double *partial, cudaStream_t s) {
+  colnorm_kernel<<<COLNORM_CTAS, 256, 0, s>>>(dd, partial);
 }
 
 // ---------------------------------------------------------------------------
@@ -920,12 +949,17 @@ void launch_residual_ss(const DeviceData &dd, int n_eval, const double *beta,
 // ---------------------------------------------------------------------------
 // K4 helpers: Rademacher probes (same bits as oracle/core.py:rademacher_probes) and dots
 // ---------------------------------------------------------------------------
-__global__ void probes_kernel(double *U, int n, int n_probes, uint64_t seed) {
+// row `row` of U holds the probes of observation perm[row] (perm == null: of observation row); rows [n, n_rows) are zero
+__global__ void probes_kernel(double *U, int n, int n_probes, uint64_t seed, const int *__restrict__ perm, int n_rows) {
   const int nb = (n_probes + 127) / 128;
   const Philox ph(seed, 0xffffffffu);
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)n * nb; idx += (size_t)gridDim.x * blockDim.x) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (size_t)n_rows * nb; idx += (size_t)gridDim.x * blockDim.x) {
     const int row = (int)(idx / nb), b = (int)(idx % nb);
-    const uint4 r = ph.raw((uint32_t)row, SLOT_PROBE, (uint32_t)b, 0xffffffffu);
+    if (row >= n) {
+      for (int p = 128 * b; p < min(n_probes, 128 * b + 128); ++p) U[(size_t)row * n_probes + p] = 0.0;
+      continue;
+    }
+    const uint4 r = ph.raw((uint32_t)(perm ? perm[row] : row), SLOT_PROBE, (uint32_t)b, 0xffffffffu);
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
     for (int k = 0; k < 4; ++k)
       for (int j = 0; j < 32; ++j) {
@@ -935,8 +969,8 @@ __global__ void probes_kernel(double *U, int n, int n_probes, uint64_t seed) {
   }
 }
 
-void launch_probes(double *U, int n, int n_probes, uint64_t seed, cudaStream_t s) {
-  probes_kernel<<<592, 256, 0, s>>>(U, n, n_probes, seed);
+void launch_probes(double *U, int n, int n_probes, uint64_t seed, cudaStream_t s, const int *perm, int n_rows) {
+  probes_kernel<<<592, 256, 0, s>>>(U, n, n_probes, seed, perm, n_rows > n ? n_rows : n);
 }
 
 constexpr int DOT_GRID = 592;
