@@ -59,15 +59,35 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 5 ms from a thread (the timed region of the
+    default run is ~30 ms -- `nvidia-smi -lms` does not even start in that time); nvidia-smi only if pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, threading.Event()
+        self.sm, self.bits, self.max_mhz, self.thread = [], 0, None, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # the process may see a subset of the GPUs: NVML enumerates all of them, so go by the visible device's UUID order
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    idx = int(ids[self.index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -75,11 +95,32 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(1.0)
+            n = self.nvml
+            names = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+            reasons = sorted(k for k, bit in names.items() if self.bits & int(bit))
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(self.sm), "source": "nvml, 5 ms polls over the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -89,7 +130,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def make_cfg4(n=N_OBS):

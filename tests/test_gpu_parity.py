@@ -145,6 +145,28 @@ def test_chain_trajectory_matches_oracle(model, prior):
     assert relnorm(got, ref) < 1e-7
 
 
+@pytest.mark.parametrize("model,own_psi", [("slx", False), ("sdm", False), ("sdm", True), ("sdem", False), ("sdem", True)])
+def test_slx_family_with_fixed_connectivity(model, own_psi):
+    """SLX / SDM / SDEM (R/40_setup.R:99-120): X <- [X, Psi_SLX %*% X_SLX] at set-up (R/12_slx.R:60-68), Psi_SLX = the model's W by
+    default or a matrix of its own (`nnz_slx` of the C ABI).  The CUDA chain follows the oracle draw by draw."""
+    from bsreg_b200 import capi
+    from bsreg_b200.synthetic import knn_weights
+    from oracle.sampler import PhiloxRNG, RefChain
+    from tests.helpers import MODEL_CODE
+    p = small_problem(model, n=480, k=3)
+    Xl = np.random.default_rng(5).standard_normal((len(p.y), 2))
+    W_slx = knn_weights(len(p.y), 4, seed=77)[0] if own_psi else None
+    n_burn, n_save, chain_id = 40, 60, 2
+    ch = RefChain(model, p.y, p.X, W=p.W, X_slx=Xl, W_slx=W_slx, rng=PhiloxRNG(21, chain_id))
+    ref = oracle_draws(ch, n_save, n_burn)
+    nodes = core.eigen_nodes(p.W, 1) if model != "slx" else None
+    with capi.Handle(p.y, p.X, model=MODEL_CODE[model], W=p.W, X_slx=Xl, W_slx=W_slx, nodes=nodes, n_chains=1,
+                     chain_offset=chain_id, seed=21) as h:
+        got = h.run(n_burn, n_save)[0].T
+    assert got.shape == ref.shape == (n_save, 3 + 2 + 1 + (model != "slx"))
+    assert relnorm(got, ref) < 1e-7
+
+
 def test_chain_batching_and_modes_are_invariant():
     """Draws of a chain id do not depend on batching, chain_offset or stats mode."""
     from bsreg_b200 import capi
