@@ -332,6 +332,15 @@ int enqueue_iterations(bsreg_handle *h, Shard &s, int count, const RunCtl &ctl) 
     h->launches += 1;
     return BSREG_OK;
   }
+  if (!streamed && count > 1 && chain_step_loops(s.dd, h->pr)) {
+    // cached statistics, general chain kernel: the whole block in ONE launch (the kernel loops; its code stays in the
+    // instruction cache from the second iteration on)
+    s.dd.gcur = (int)((s.seq + 2) % 3);          // buffer of the latest sweep, as enqueue_chain_step
+    launch_chain_step(s.dd, h->pr, s.cs, s.ctl_dev, s.draws_dev, s.stream, count);
+    ++h->launches;
+    CU(cudaGetLastError());
+    return BSREG_OK;
+  }
   const int per_iter = streamed ? 2 : 1;
   while (count > 0) {
     if (count >= GRAPH_UNROLL && (!streamed || s.seq % 3 == 0)) {

@@ -23,7 +23,7 @@ namespace bsreg {
 
 template <int NT>
 __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, ChainState cs, const RunCtl *ctlp,
-                                                   double *draws, int mode, InitArgs ia) {
+                                                   double *draws, int mode, InitArgs ia, int nrep) {
   extern __shared__ double sm[];
   const int c = blockIdx.x, tid = threadIdx.x, m = dd.m, n = dd.n;
   const int A = aux_len(m), ld = work_ld(m);
@@ -36,7 +36,13 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
   double *vecA = aux, *vecB = aux + m;
   const Philox ph(cs.seed, (uint32_t)(cs.chain_offset + c));
 
+  // nrep > 1 (cached statistics: the Gram matrix does not change): that many Gibbs iterations in one launch.  The state goes
+  // through global memory between them exactly as between launches; the loop saves the launches (38 -> 35 us per iteration
+  // at M = 20, SAR + Conjugate: the step itself is bound by its dependent FP64 arithmetic, profiles/r2_chain_general_trace.log).
+  for (int rep = 0; rep < nrep; ++rep) {
+  if (rep > 0) { __threadfence_block(); bsync<NT>(); }
   double sigma2, lam, scale_l, scale_t;
+  TRACE(16);
   long long cnt[2][4];
   uint32_t it;
   const int step0 = (mode == MODE_STEP) ? cs.step[c] : 0;
@@ -98,6 +104,7 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
     it = (uint32_t)(iters + 1);
     bsync<NT>();
   }
+  TRACE(17);
 
   const bool do_sweep = (mode == MODE_STEP) || (mode == MODE_INIT && conj);   // Conjugate starts with one beta, sigma draw
   const bool reuse = sar && pr.prior == 0;     // P0 and sigma^2 unchanged between the beta and lambda steps
@@ -109,9 +116,11 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
       const double rss = resid_ss<NT>(g, conj ? w.mu1 : w.beta, lam, m, w.red);
       sigma2 = 1.0 / ph.gamma(it, SLOT_SIGMA, pr.shape1, pr.rate0 + 0.5 * rss);
     }
+    TRACE(18);
     // ---- sample_beta ----
     const int nrhs = reuse ? 3 : 1;
     factor_system<NT>(g, w, lam, conj ? 1.0 : sigma2, m, nrhs, 0);
+    TRACE(19);
     for (int a = tid; a < m; a += NT) w.eps[a] = ph.normal(it, SLOT_BETA, (uint32_t)a);
     bsync<NT>();
     for (int j = tid; j < m; j += NT) {
@@ -132,6 +141,7 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
     }
   }
 
+  TRACE(20);
   if (mode == MODE_STEP) {
     // ---- sample_shrinkage ----
     if (hs) {
@@ -186,6 +196,7 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
     }
   }
 
+  TRACE(21);
   // ---- spatial parameter ----
   double ldet_cur = aux[2 * m + 2], rss_cur = aux[2 * m + 3];
   if (mode != MODE_STEP && (sar || sem)) {
@@ -202,8 +213,10 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
       }
       bsync<NT>();
     }
+    TRACE(22);
     double e0e0, e1e0, e1e1;
     sar_coeffs<NT>(g, w, m, e0e0, e1e0, e1e1);
+    TRACE(23);
     const double prop = ph.truncated_rw(it, SLOT_LAMBDA_PROP, lam, scale_l, pr.lam_lo, pr.lam_hi);
     const double ldet_prop = logdet_nodes<NT>(dd, prop, w.red);
     const double rss_p = e0e0 - 2.0 * prop * e1e0 + prop * prop * e1e1;
@@ -222,6 +235,7 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
     mh_count(cnt[0], acc);
   }
 
+  TRACE(24);
   // ---- finalize, tuning, draw store ----
   if (mode == MODE_STEP) {
     iters += 1;
@@ -259,6 +273,8 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
       for (int q = 0; q < 4; ++q) cs.mh_cnt[(size_t)c * 8 + k * 4 + q] = cnt[k][q];
     cs.iters[c] = iters;
     aux[2 * m + 2] = ldet_cur; aux[2 * m + 3] = rss_cur;
+  }
+  TRACE(25);
   }
 }
 
@@ -541,7 +557,7 @@ __global__ void __launch_bounds__(FAST_NT) chain_fast_kernel(DeviceData dd, Prio
 }
 
 #ifdef BSREG_TRACE
-extern "C" int bsreg_debug_trace(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 32); }
+extern "C" int bsreg_debug_trace(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 64); }
 #endif
 
 bool chain_fast_supported(const DeviceData &dd, const Priors &pr) {
@@ -549,20 +565,25 @@ bool chain_fast_supported(const DeviceData &dd, const Priors &pr) {
 }
 
 size_t chain_smem_bytes(int m, int model, int) { return work_doubles(m, model) * sizeof(double); }
-int chain_threads(int m) { return m <= 32 ? 32 : 128; }
+int chain_threads(int m) {
+  static const int forced = getenv("BSREG_CHAIN_NT") ? atoi(getenv("BSREG_CHAIN_NT")) : 0;   // A/B switch: 32 or 128
+  if (forced == 128 || (forced == 32 && m <= 32)) return forced;
+  // four warps from M = 12 on: one bordered row per thread (2M + 3 rows); M = 20 SAR + Horseshoe: 54 -> 40 us per step
+  return m < 12 ? 32 : 128;
+}
 
 template <int NT>
 static void launch_chain_nt(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl *ctl, double *draws,
-                            int mode, const InitArgs &ia, cudaStream_t s) {
+                            int mode, const InitArgs &ia, cudaStream_t s, int nrep) {
   const size_t smem = chain_smem_bytes(dd.m, dd.model, pr.prior);
   if (smem_optin((const void *)chain_kernel<NT>, smem) != cudaSuccess) return;   // the error stays pending for cudaGetLastError
-  chain_kernel<NT><<<cs.n_chains, NT, smem, s>>>(dd, pr, cs, ctl, draws, mode, ia);
+  chain_kernel<NT><<<cs.n_chains, NT, smem, s>>>(dd, pr, cs, ctl, draws, mode, ia, nrep);
 }
 
 static void launch_chain(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl *ctl, double *draws,
-                         int mode, const InitArgs &ia, cudaStream_t s) {
-  if (chain_threads(dd.m) == 32) launch_chain_nt<32>(dd, pr, cs, ctl, draws, mode, ia, s);
-  else launch_chain_nt<128>(dd, pr, cs, ctl, draws, mode, ia, s);
+                         int mode, const InitArgs &ia, cudaStream_t s, int nrep = 1) {
+  if (chain_threads(dd.m) == 32) launch_chain_nt<32>(dd, pr, cs, ctl, draws, mode, ia, s, nrep);
+  else launch_chain_nt<128>(dd, pr, cs, ctl, draws, mode, ia, s, nrep);
 }
 
 void launch_chain_init(const DeviceData &dd, const Priors &pr, const ChainState &cs, const ChainInit &ci, cudaStream_t s) {
@@ -571,16 +592,25 @@ void launch_chain_init(const DeviceData &dd, const Priors &pr, const ChainState 
   launch_chain(dd, pr, cs, nullptr, nullptr, ci.refresh_only ? MODE_REFRESH : MODE_INIT, ia, s);
 }
 
-void launch_chain_step(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl *ctl, double *draws,
-                       cudaStream_t s) {
+static bool chain_uses_fast(const DeviceData &dd, const Priors &pr) {
   static const bool no_fast = getenv("BSREG_CHAIN_GENERIC") != nullptr;   // A/B switch for tests and profiling
-  if (!no_fast && chain_fast_supported(dd, pr)) {
+  return !no_fast && chain_fast_supported(dd, pr);
+}
+
+bool chain_step_loops(const DeviceData &dd, const Priors &pr) {
+  static const bool off = getenv("BSREG_NO_CHAIN_LOOP") != nullptr;       // A/B switch
+  return !off && !chain_uses_fast(dd, pr) && dd.Gchain == nullptr;
+}
+
+void launch_chain_step(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl *ctl, double *draws,
+                       cudaStream_t s, int nrep) {
+  if (chain_uses_fast(dd, pr)) {
     if (dd.m <= 24) chain_fast_kernel<24><<<cs.n_chains, FAST_NT, fast_doubles<24>(dd.m, dd.model) * sizeof(double), s>>>(dd, pr, cs, ctl, draws);
     else chain_fast_kernel<32><<<cs.n_chains, FAST_NT, fast_doubles<32>(dd.m, dd.model) * sizeof(double), s>>>(dd, pr, cs, ctl, draws);
     return;
   }
   InitArgs ia{};
-  launch_chain(dd, pr, cs, ctl, draws, MODE_STEP, ia, s);
+  launch_chain(dd, pr, cs, ctl, draws, MODE_STEP, ia, s, nrep);
 }
 
 // ---------------------------------------------------------------------------

@@ -7,6 +7,15 @@ namespace bsreg {
 
 enum { MODE_STEP = 0, MODE_INIT = 1, MODE_REFRESH = 2 };
 
+#ifdef BSREG_TRACE
+static __device__ long long g_trace[64];
+#define TRACE(i) do { if (blockIdx.x == 0 && tid == 0) g_trace[i] = clock64(); } while (0)
+#define FTRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_trace[i] = clock64(); } while (0)
+#else
+#define TRACE(i) do { } while (0)
+#define FTRACE(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ double warp_sum_c(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -73,6 +82,11 @@ struct GView {
 
 // ---- bordered Cholesky: rows [0,m) = A (lower), rows [m,nrows) = extra rows B'.
 // On exit rows [0,m) hold L (A = L L'), extra row r holds (L^-1 b_r)'. nrows <= 3*NT.
+// Left-looking: a dot product of length k per row and column, two block barriers per column.  (Round 2 tried right-looking
+// forms with ONE barrier per column, the reciprocal square root of the pivot computed by every thread and the row updated in
+// shared memory or held in registers: 23 500 / 18 400 cycles per factorisation at M = 20 against 20 600 for this one with four
+// warps -- a column costs ~470 cycles of pivot arithmetic and ~500 of row update whichever way it is written
+// (profiles/r2_chain_general_trace.log); not kept.)
 template <int NT>
 __device__ void chol_bordered(double *T, double *dg, int m, int nrows, int ld, int tid = threadIdx.x) {
   for (int k = 0; k < m; ++k) {
@@ -189,10 +203,18 @@ __device__ __forceinline__ void stage_gram(const DeviceData &dd, double *Gs) {
 template <int NT>
 __device__ double resid_ss(const GView &g, const double *b, double lam, int m, double *red) {
   double part = 0.0;
-  for (int a = threadIdx.x; a < m; a += NT) {
-    double t = 0.0;
-    for (int c = 0; c < m; ++c) t = fma(g.xx_eff(a, c, lam), b[c], t);
-    part = fma(b[a], t - 2.0 * g.xy_eff(a, lam), part);
+  if (NT > 32) {                       // the m x m products over all threads (fixed assignment, fixed-order block sum)
+    for (int e = threadIdx.x; e < m * m; e += NT) {
+      const int a = e / m, c = e - a * m;
+      part = fma(b[a] * g.xx_eff(a, c, lam), b[c], part);
+    }
+    for (int a = threadIdx.x; a < m; a += NT) part = fma(-2.0 * b[a], g.xy_eff(a, lam), part);
+  } else {
+    for (int a = threadIdx.x; a < m; a += NT) {
+      double t = 0.0;
+      for (int c = 0; c < m; ++c) t = fma(g.xx_eff(a, c, lam), b[c], t);
+      part = fma(b[a], t - 2.0 * g.xy_eff(a, lam), part);
+    }
   }
   return g.yy_eff(lam) + bsum<NT>(part, red);
 }
@@ -212,21 +234,24 @@ __device__ void fill_identity(double *T, int row0, int m, int ld) {
 template <int NT>
 __device__ void factor_system(const GView &g, Work &w, double lam_eff, double s, int m, int nrhs, int first_rhs_kind) {
   const int ld = work_ld(m);
+  const double si = 1.0 / s;
   for (int e = threadIdx.x; e < m * m; e += NT) {
     const int a = e / m, b = e - a * m;
-    if (b <= a) w.T[a * ld + b] = g.xx_eff(a, b, lam_eff) / s + (a == b ? w.p0[a] : 0.0);
+    if (b <= a) w.T[a * ld + b] = fma(g.xx_eff(a, b, lam_eff), si, a == b ? w.p0[a] : 0.0);
   }
   for (int e = threadIdx.x; e < nrhs * m; e += NT) {
     const int t = e / m, a = e - t * m;
     const int kind = first_rhs_kind + t;
     double v;
-    if (kind == 0) v = g.xy_eff(a, lam_eff) / s + w.p0[a] * w.mu0[a];
-    else if (kind == 1) v = w.p0[a] * w.mu0[a] + g.Xy(a) / s;
-    else v = w.p0[a] * w.mu0[a] + g.XWy(a) / s;
+    if (kind == 0) v = fma(g.xy_eff(a, lam_eff), si, w.p0[a] * w.mu0[a]);
+    else if (kind == 1) v = fma(g.Xy(a), si, w.p0[a] * w.mu0[a]);
+    else v = fma(g.XWy(a), si, w.p0[a] * w.mu0[a]);
     w.T[(m + t) * ld + a] = v;
   }
+  if (first_rhs_kind == 0) FTRACE(26);
   fill_identity<NT>(w.T, m + nrhs, m, ld);
   bsync<NT>();
+  if (first_rhs_kind == 0) FTRACE(27);
   chol_bordered<NT>(w.T, w.dg, m, 2 * m + nrhs, ld);
 }
 
@@ -287,12 +312,6 @@ struct InitArgs {
 };
 
 
-#ifdef BSREG_TRACE
-static __device__ long long g_trace[64];
-#define TRACE(i) do { if (blockIdx.x == 0 && tid == 0) g_trace[i] = clock64(); } while (0)
-#else
-#define TRACE(i) do { } while (0)
-#endif
 constexpr int FAST_MAX_M = 30;          // 2M + 3 bordered rows fit two warps
 constexpr int FAST_NT = 128;
 

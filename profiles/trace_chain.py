@@ -15,7 +15,7 @@ with capi.Handle(p.y, p.X, model=capi.MODEL_SAR, W=p.W, ldet=capi.LDET_CHEBYSHEV
     h.run(100, 0)
     h.launch_chain_step(5)
     h.sync()
-    out = np.zeros(32, dtype=np.int64)
+    out = np.zeros(64, dtype=np.int64)
     capi.load().bsreg_debug_trace(out.ctypes.data_as(C.c_void_p))
     # thread 0 (critical-path warp) passes points 0,1,3..9; point 2 belongs to warp 3 and is not recorded by tid 0
     names = {1: "loads+sync", 2: "stage rows", 3: "row load + sigma2 wait", 4: "LDL elimination", 5: "Yd store + sync", 6: "dots + beta",

@@ -145,6 +145,21 @@ def test_chain_trajectory_matches_oracle(model, prior):
     assert relnorm(got, ref) < 1e-7
 
 
+@pytest.mark.parametrize("model,prior,k", [("sar", "Horseshoe", 14), ("sar", "Shrinkage", 20), ("lm", "Conjugate", 16),
+                                           ("sem", "Horseshoe", 13), ("sar", "Conjugate", 26), ("sem", "Shrinkage", 22)])
+def test_general_chain_step_wide_designs(model, prior, k):
+    """From M = 12 on the general chain step runs with four warps (one bordered row of the factorisation per thread, block-wide
+    reductions): same trajectories as the oracle; M = 26 still one row per thread, three right-hand sides."""
+    p = small_problem(model, n=600, k=k)
+    priors = {"SNG": dict(theta_scale=0.3)} if prior == "Shrinkage" else {}
+    n_burn, n_save, chain_id = 30, 50, 1
+    ref = oracle_draws(oracle_chain(model, p, prior, priors, seed=7, chain=chain_id), n_save, n_burn)
+    with cuda_handle(model, p, prior, priors, seed=7, n_chains=2, chain_offset=chain_id - 1) as h:
+        got = h.run(n_burn, n_save)[1].T
+    assert got.shape == ref.shape
+    assert relnorm(got, ref) < 1e-7
+
+
 @pytest.mark.parametrize("model,own_psi", [("slx", False), ("sdm", False), ("sdm", True), ("sdem", False), ("sdem", True)])
 def test_slx_family_with_fixed_connectivity(model, own_psi):
     """SLX / SDM / SDEM (R/40_setup.R:99-120): X <- [X, Psi_SLX %*% X_SLX] at set-up (R/12_slx.R:60-68), Psi_SLX = the model's W by
