@@ -59,78 +59,52 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region: NVML polled every 5 ms from a thread (the timed region of the
-    default run is ~30 ms -- `nvidia-smi -lms` does not even start in that time); nvidia-smi only if pynvml is missing."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """SM clock and throttle reasons DURING the timed region.  `nvidia-smi -lms 20` runs as a process of its own (NVML inside
+    this process crashed ncu when the bench was profiled); it needs ~0.2 s to start and the timed region of the default run is
+    ~30 ms, so it is started before the warm-up steps and the rows are cut to the timed region by their timestamps (the last
+    warm-up steps run the same kernel, so if fewer than two rows fall inside, the rows of the warm-up are kept as well and
+    `window` says so)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, threading.Event()
-        self.sm, self.bits, self.max_mhz, self.thread = [], 0, None, None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            # the process may see a subset of the GPUs: NVML enumerates all of them, so go by the visible device's UUID order
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = self.index
-            if vis:
-                ids = [v.strip() for v in vis.split(",") if v.strip()]
-                if self.index < len(ids) and ids[self.index].isdigit():
-                    idx = int(ids[self.index])
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
-            self.nvml = pynvml
-            self.thread = threading.Thread(target=self._poll, daemon=True)
-            self.thread.start()
-            return
-        except Exception:
-            self.nvml = None
-        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
-    def _poll(self):
-        n = self.nvml
-        while not self.stop_flag.is_set():
-            try:
-                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
-                self.bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-            except Exception:
-                pass
-            time.sleep(0.005)
-
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
-        if self.nvml is not None:
-            self.stop_flag.set()
-            self.thread.join(1.0)
-            n = self.nvml
-            names = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
-                     "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
-                     "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
-                     "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
-            reasons = sorted(k for k, bit in names.items() if self.bits & int(bit))
-            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
-                    "reasons": reasons, "samples": len(self.sm), "source": "nvml, 5 ms polls over the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in ok if self.t0 is not None and self.t0 - 0.02 <= t <= (self.t1 or t) + 0.02]
+        window = "timed region"
+        if len(inside) < 2:
+            inside, window = [r for _, r in ok], "warm-up + timed region (same kernel)"
+        sm = [float(r[1]) for r in inside]
+        mx = [float(r[2]) for r in inside if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in inside for i in range(4) if r[4 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
+                "reasons": reasons, "samples": len(sm), "window": window, "source": "nvidia-smi -lms 20"}
 
 
 def make_cfg4(n=N_OBS):
@@ -280,14 +254,17 @@ def run_ours(args):
         return [a.elapsed_time(b) for a, b in ev]
 
     # ---- device-resident throughput ----
-    timed_steps(h, args.warmup)
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        time.sleep(0.3)                                       # nvidia-smi is up before the warm-up steps begin
+    timed_steps(h, args.warmup)
+    barrier()
+    clocks.mark_begin()
     l0 = h.kernel_launches()
     ms = timed_steps(h, args.steps)
     launches = h.kernel_launches() - l0
+    clocks.mark_end()
     barrier()
     clk = clocks.stop() if rank == 0 else None
     total_ms = float(sum(ms))

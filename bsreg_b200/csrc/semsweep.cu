@@ -248,8 +248,9 @@ __global__ void __launch_bounds__(SEM_T, 1) sweep_sem_kernel(DeviceData dd, SemG
             for (int u = 0; u < wt; ++u) body(VA[u * R + i], CI[u * R + i]);
           } else {
             const int p0 = RP[i], len = RP[i + 1] - p0;
-            const int maxlen = __reduce_max_sync(0xffffffffu, len);
-            for (int u = 0; u < maxlen; ++u) {
+            // (a vote per step, not redux.sync for the longest row: ncu could not prepare the kernel with REDUX in it, and
+            // a shuffle reduction here doubled the time of the whole kernel, 257 -> 490 us)
+            for (int u = 0; __any_sync(0xffffffffu, u < len); ++u) {
               const bool on = u < len;
               body(on ? VA[p0 + u] : 0.0, on ? CI[p0 + u] : 0);
             }
