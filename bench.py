@@ -255,7 +255,7 @@ def run_ours(args):
 
     # ---- device-resident throughput ----
     clocks = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         clocks.start()
         time.sleep(0.3)                                       # nvidia-smi is up before the warm-up steps begin
     timed_steps(h, args.warmup)
@@ -534,6 +534,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-big", action="store_true", help="skip the N = 1e6 HBM-resident check (saves ~25 s)")
     ap.add_argument("--skip-cpu", action="store_true", help="shrink the CPU baseline sample to 40 iterations (profiler runs)")
+    ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi (runs under ncu: a launch list, never a bench value)")
     ap.add_argument("--ref-iters", type=int, default=300, help="iterations per chain and step of the reference arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
