@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
         for (int a = tid; a < m; a += NT) w.T[m * ld + a] = g.xy_eff(a, lam);
         fill_identity<NT>(w.T, m + 1, m, ld);
         bsync<NT>();
-        chol_bordered<NT>(w.T, w.dg, m, 2 * m + 1, ld);
+        chol_bordered<NT>(w.T, w.dg, w.pub, m, 2 * m + 1, ld);
         for (int j = tid; j < m; j += NT) w.beta[j] = upper_dot(w.T + (m + 1 + j) * ld, w.T + m * ld, j, m);
       }
       bsync<NT>();
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(FAST_NT) chain_fast_kernel(DeviceData dd, Prio
         }
         for (int r = lane; r < m; r += 32) T2[m * ld + r] = g.xy_eff(r, prop);
         __syncwarp();
-        chol_bordered<32>(T2, t0, m, m + 1, ld, lane);               // t0 is free until phase 3 (SAR only)
+        chol_bordered_ll<32>(T2, t0, m, m + 1, ld, lane);               // t0 is free until phase 3 (SAR only)
         double q2 = 0.0;
         for (int r = lane; r < m; r += 32) { const double q = T2[m * ld + r]; q2 = fma(q, q, q2); }
         const double r = g.yy_eff(prop) - warp_sum_c(q2);

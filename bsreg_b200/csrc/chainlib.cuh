@@ -82,13 +82,9 @@ struct GView {
 
 // ---- bordered Cholesky: rows [0,m) = A (lower), rows [m,nrows) = extra rows B'.
 // On exit rows [0,m) hold L (A = L L'), extra row r holds (L^-1 b_r)'. nrows <= 3*NT.
-// Left-looking: a dot product of length k per row and column, two block barriers per column.  (Round 2 tried right-looking
-// forms with ONE barrier per column, the reciprocal square root of the pivot computed by every thread and the row updated in
-// shared memory or held in registers: 23 500 / 18 400 cycles per factorisation at M = 20 against 20 600 for this one with four
-// warps -- a column costs ~470 cycles of pivot arithmetic and ~500 of row update whichever way it is written
-// (profiles/r2_chain_general_trace.log); not kept.)
+// Left-looking: a dot product of length k per row and column, two block barriers per column; any m, any NT.
 template <int NT>
-__device__ void chol_bordered(double *T, double *dg, int m, int nrows, int ld, int tid = threadIdx.x) {
+__device__ void chol_bordered_ll(double *T, double *dg, int m, int nrows, int ld, int tid = threadIdx.x) {
   for (int k = 0; k < m; ++k) {
     double s[3];
 #pragma unroll
@@ -115,6 +111,59 @@ __device__ void chol_bordered(double *T, double *dg, int m, int nrows, int ld, i
     }
     bsync<NT>();
   }
+}
+
+// Right-looking form for one bordered row per thread (nrows <= NT, m <= MMAX), the row in registers: column k costs ONE
+// block barrier and no dependent chain of length k.  A dependent FP64 operation takes ~22 cycles here, so what counts is
+// the number of operations between two barriers: every thread forms the reciprocal square root of the pivot itself (from the
+// published diagonal of the pivot row: rsqrt() is one MUFU seed + a short Newton tail, ~100 cycles, where sqrt followed by a
+// division is ~180 and a hand-written Newton iteration from the single-precision seed ~470), scales its entry, the rows of A
+// publish theirs, and the trailing entries are updated with independent FMAs.  20 600 -> ~6 000 cycles per factorisation at
+// M = 20 (clock64 trace, profiles/r2_chain_general_trace.log).
+// pub: [2][MMAX + 2] doubles of shared memory (double buffered by the parity of the column).
+template <int NT, int MMAX>
+__device__ void chol_bordered_rr(double *T, double *pub, int m, int nrows, int ld) {
+  constexpr int LP = MMAX + 2;
+  const int r = threadIdx.x;
+  const bool on = r < nrows;
+  double a[MMAX];
+#pragma unroll
+  for (int j = 0; j < MMAX; ++j) a[j] = (on && j < m && (r >= m || j <= r)) ? T[r * ld + j] : 0.0;
+  double dk = T[0];
+#pragma unroll
+  for (int k = 0; k < MMAX; ++k) {
+    if (k < m) {
+      double *pb = pub + (k & 1) * LP;
+      const double rinv = rsqrt(dk);
+      const double l = r == k ? dk * rinv : a[k] * rinv;
+      a[k] = l;
+      if (r > k && r < m) pb[r] = l;
+      if (r == k + 1) pb[MMAX] = a[k + 1 < MMAX ? k + 1 : k];          // the next pivot row's diagonal, before this column's update
+      bsync<NT>();
+      if (k + 1 < m) {
+        const double l1 = pb[k + 1 < MMAX ? k + 1 : k];
+        dk = fma(-l1, l1, pb[MMAX]);                                   // the same arithmetic as row k + 1's own update below
+      }
+      if (r > k) {
+#pragma unroll
+        for (int j = k + 1; j < MMAX; ++j) a[j] = fma(-l, pb[j], a[j]);   // columns >= m carry garbage nobody reads
+      }
+    }
+  }
+  if (on) {
+#pragma unroll
+    for (int j = 0; j < MMAX; ++j) if (j < m && (r >= m || j <= r)) T[r * ld + j] = a[j];
+  }
+  bsync<NT>();
+}
+
+constexpr int CHOL_RR_MMAX = 24;
+template <int NT>
+__device__ __forceinline__ void chol_bordered(double *T, double *dg, double *pub, int m, int nrows, int ld, int tid = threadIdx.x) {
+  if constexpr (NT >= 128) {
+    if (nrows <= NT && m <= CHOL_RR_MMAX) { chol_bordered_rr<NT, CHOL_RR_MMAX>(T, pub, m, nrows, ld); return; }
+  }
+  chol_bordered_ll<NT>(T, dg, m, nrows, ld, tid);
 }
 
 // x[j] = sum_{k>=j} Y[j][k] w[k]  (Y = L^-T stored by rows, upper triangular)
@@ -163,16 +212,17 @@ __device__ __forceinline__ double logpost_lambda(double v, double ldet, double r
 
 // shared-memory workspace of one chain
 struct Work {
-  double *T, *dg, *p0, *mu0, *beta, *mu1, *b0, *b1, *eps, *t0, *t1, *red, *G;
+  double *T, *dg, *p0, *mu0, *beta, *mu1, *b0, *b1, *eps, *t0, *t1, *red, *pub, *G;
 };
 
 constexpr int G_STAGE_MAX_D = 48;     // stage G in shared memory up to this Gram dimension (18 KB)
 __host__ __device__ inline int gram_dim(int m, int model) { return model == 2 ? 2 * m + 2 : m + 2; }
 __host__ __device__ inline bool g_staged(int m, int model) { return gram_dim(m, model) <= G_STAGE_MAX_D; }
 __host__ __device__ inline int work_ld(int m) { return m | 1; }
+constexpr int CHOL_PUB = 2 * (24 + 2);   // published column + next pivot's diagonal of the right-looking factorisation, double buffered
 __host__ __device__ inline size_t work_doubles(int m, int model) {
   const size_t d = gram_dim(m, model);
-  return (size_t)(2 * m + 3) * work_ld(m) + 10 * (size_t)m + 16 + (g_staged(m, model) ? d * d : 0);
+  return (size_t)(2 * m + 3) * work_ld(m) + 10 * (size_t)m + 16 + CHOL_PUB + (g_staged(m, model) ? d * d : 0);
 }
 
 __device__ __forceinline__ Work carve(double *sm, int m, int model) {
@@ -182,7 +232,8 @@ __device__ __forceinline__ Work carve(double *sm, int m, int model) {
   w.p0 = w.dg + m; w.mu0 = w.p0 + m; w.beta = w.mu0 + m; w.mu1 = w.beta + m;
   w.b0 = w.mu1 + m; w.b1 = w.b0 + m; w.eps = w.b1 + m; w.t0 = w.eps + m; w.t1 = w.t0 + m;
   w.red = w.t1 + m;
-  w.G = g_staged(m, model) ? w.red + 16 : nullptr;
+  w.pub = w.red + 16;
+  w.G = g_staged(m, model) ? w.pub + CHOL_PUB : nullptr;
   return w;
 }
 
@@ -235,24 +286,24 @@ template <int NT>
 __device__ void factor_system(const GView &g, Work &w, double lam_eff, double s, int m, int nrhs, int first_rhs_kind) {
   const int ld = work_ld(m);
   const double si = 1.0 / s;
+  auto rhs_value = [&](int kind, int a) {
+    if (kind == 0) return fma(g.xy_eff(a, lam_eff), si, w.p0[a] * w.mu0[a]);
+    if (kind == 1) return fma(g.Xy(a), si, w.p0[a] * w.mu0[a]);
+    return fma(g.XWy(a), si, w.p0[a] * w.mu0[a]);
+  };
   for (int e = threadIdx.x; e < m * m; e += NT) {
     const int a = e / m, b = e - a * m;
     if (b <= a) w.T[a * ld + b] = fma(g.xx_eff(a, b, lam_eff), si, a == b ? w.p0[a] : 0.0);
   }
   for (int e = threadIdx.x; e < nrhs * m; e += NT) {
     const int t = e / m, a = e - t * m;
-    const int kind = first_rhs_kind + t;
-    double v;
-    if (kind == 0) v = fma(g.xy_eff(a, lam_eff), si, w.p0[a] * w.mu0[a]);
-    else if (kind == 1) v = fma(g.Xy(a), si, w.p0[a] * w.mu0[a]);
-    else v = fma(g.XWy(a), si, w.p0[a] * w.mu0[a]);
-    w.T[(m + t) * ld + a] = v;
+    w.T[(m + t) * ld + a] = rhs_value(first_rhs_kind + t, a);
   }
   if (first_rhs_kind == 0) FTRACE(26);
   fill_identity<NT>(w.T, m + nrhs, m, ld);
   bsync<NT>();
   if (first_rhs_kind == 0) FTRACE(27);
-  chol_bordered<NT>(w.T, w.dg, m, 2 * m + nrhs, ld);
+  chol_bordered<NT>(w.T, w.dg, w.pub, m, 2 * m + nrhs, ld);
 }
 
 // SAR: coefficients of rss(v) = e0e0 - 2 v e1e0 + v^2 e1e1 from b0, b1 (R/15_sar.R:110-115)
@@ -285,7 +336,7 @@ __device__ double sem_rss(const GView &g, Work &w, double v, int m) {
   }
   for (int a = threadIdx.x; a < m; a += NT) w.T[m * ld + a] = g.xy_eff(a, v);
   bsync<NT>();
-  chol_bordered<NT>(w.T, w.dg, m, m + 1, ld);
+  chol_bordered<NT>(w.T, w.dg, w.pub, m, m + 1, ld);
   double part = 0.0;
   for (int a = threadIdx.x; a < m; a += NT) { const double q = w.T[m * ld + a]; part = fma(q, q, part); }
   return g.yy_eff(v) - bsum<NT>(part, w.red);
