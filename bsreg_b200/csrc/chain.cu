@@ -598,7 +598,7 @@ static bool chain_uses_fast(const DeviceData &dd, const Priors &pr) {
 }
 
 bool chain_step_loops(const DeviceData &dd, const Priors &pr) {
-  static const bool off = getenv("BSREG_NO_CHAIN_LOOP") != nullptr;       // A/B switch
+  const bool off = getenv("BSREG_NO_CHAIN_LOOP") != nullptr;              // A/B switch (read per call: tests flip it)
   return !off && !chain_uses_fast(dd, pr) && dd.Gchain == nullptr;
 }
 

@@ -160,6 +160,29 @@ def test_general_chain_step_wide_designs(model, prior, k):
     assert relnorm(got, ref) < 1e-7
 
 
+@pytest.mark.parametrize("model,prior,k", [("sar", "Horseshoe", 14), ("lm", "Shrinkage", 12), ("sem", "Conjugate", 5)])
+def test_looped_chain_kernel_equals_one_launch_per_step(model, prior, k, monkeypatch):
+    """With cached statistics the general chain kernel runs a whole block of iterations in one launch (csrc/chain.cu, nrep):
+    the draws must be bit-identical to one launch per step (BSREG_NO_CHAIN_LOOP), to the streamed run (the sweeps
+    recompute the same Gram matrix), and must not depend on how the run is cut into blocks."""
+    from bsreg_b200 import capi
+    p = small_problem(model, n=500, k=k)
+    priors = {"SNG": dict(theta_scale=0.3)} if prior == "Shrinkage" else {}
+    kw = dict(seed=13, n_chains=3)
+    with cuda_handle(model, p, prior, priors, stats_mode=capi.STATS_CACHED, **kw) as h:
+        looped = h.run(25, 35)
+    with cuda_handle(model, p, prior, priors, stats_mode=capi.STATS_CACHED, **kw) as h:
+        a = h.run(25, 10)
+        b = h.run(0, 1)
+        c = h.run(0, 24)
+    assert np.array_equal(np.concatenate([a, b, c], axis=2), looped)
+    with cuda_handle(model, p, prior, priors, stats_mode=capi.STATS_STREAM, **kw) as h:
+        assert np.array_equal(h.run(25, 35), looped)
+    monkeypatch.setenv("BSREG_NO_CHAIN_LOOP", "1")
+    with cuda_handle(model, p, prior, priors, stats_mode=capi.STATS_CACHED, **kw) as h:
+        assert np.array_equal(h.run(25, 35), looped)
+
+
 @pytest.mark.parametrize("model,own_psi", [("slx", False), ("sdm", False), ("sdm", True), ("sdem", False), ("sdem", True)])
 def test_slx_family_with_fixed_connectivity(model, own_psi):
     """SLX / SDM / SDEM (R/40_setup.R:99-120): X <- [X, Psi_SLX %*% X_SLX] at set-up (R/12_slx.R:60-68), Psi_SLX = the model's W by
