@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(NT) chain_kernel(DeviceData dd, Priors pr, Cha
 // per column: publish the column, one barrier, reciprocal of the pivot, rank-1 update.
 template <int MMAX>
 __global__ void __launch_bounds__(FAST_NT) chain_fast_kernel(DeviceData dd, Priors pr, ChainState cs, const RunCtl *ctlp,
-                                                            double *draws) {
+                                                            double *draws, int nrep) {
   extern __shared__ double sm[];
   const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, m = dd.m, n = dd.n, d = dd.d;
   const int ld = work_ld(m), A = aux_len(m);
@@ -311,6 +311,10 @@ __global__ void __launch_bounds__(FAST_NT) chain_fast_kernel(DeviceData dd, Prio
   const GView g{G, nullptr, nullptr, d, m, dd.model};
   const int nrhs = sar ? 3 : 1, nrows = 2 * m + nrhs;
 
+  // nrep > 1 (cached statistics): that many iterations in one launch, the state going through global memory between them as
+  // between launches; the Gram matrix is staged once
+  for (int rep = 0; rep < nrep; ++rep) {
+  if (rep > 0) { __threadfence_block(); __syncthreads(); }
   TRACE(0);
   // ---- phase 0: one round trip to L2 for the state and the Gram matrix; warp 2 draws meanwhile ----
   const long long iters0 = cs.iters[c];
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(FAST_NT) chain_fast_kernel(DeviceData dd, Prio
   } else {
     const int t3 = wid == 3 ? 64 + lane : tid;                       // 96 staging threads
     const long long *gf = dd.Gfix + (size_t)dd.gcur * d * d;
-    for (int i = t3 >> 5; i < d; i += 3)
+    for (int i = t3 >> 5; i < (rep == 0 ? d : 0); i += 3)
       for (int j = lane; j < d; j += 32) {
         const int e = i <= j ? i * d + j : j * d + i;
         G[i * d + j] = (double)gf[e] * dd.Gscale[e];
@@ -554,6 +558,7 @@ __global__ void __launch_bounds__(FAST_NT) chain_fast_kernel(DeviceData dd, Prio
     aux[2 * m + 2] = ldet_cur; aux[2 * m + 3] = rss_cur;
   }
   TRACE(9);
+  }
 }
 
 #ifdef BSREG_TRACE
@@ -599,14 +604,14 @@ static bool chain_uses_fast(const DeviceData &dd, const Priors &pr) {
 
 bool chain_step_loops(const DeviceData &dd, const Priors &pr) {
   const bool off = getenv("BSREG_NO_CHAIN_LOOP") != nullptr;              // A/B switch (read per call: tests flip it)
-  return !off && !chain_uses_fast(dd, pr) && dd.Gchain == nullptr;
+  return !off && dd.Gchain == nullptr;
 }
 
 void launch_chain_step(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl *ctl, double *draws,
                        cudaStream_t s, int nrep) {
   if (chain_uses_fast(dd, pr)) {
-    if (dd.m <= 24) chain_fast_kernel<24><<<cs.n_chains, FAST_NT, fast_doubles<24>(dd.m, dd.model) * sizeof(double), s>>>(dd, pr, cs, ctl, draws);
-    else chain_fast_kernel<32><<<cs.n_chains, FAST_NT, fast_doubles<32>(dd.m, dd.model) * sizeof(double), s>>>(dd, pr, cs, ctl, draws);
+    if (dd.m <= 24) chain_fast_kernel<24><<<cs.n_chains, FAST_NT, fast_doubles<24>(dd.m, dd.model) * sizeof(double), s>>>(dd, pr, cs, ctl, draws, nrep);
+    else chain_fast_kernel<32><<<cs.n_chains, FAST_NT, fast_doubles<32>(dd.m, dd.model) * sizeof(double), s>>>(dd, pr, cs, ctl, draws, nrep);
     return;
   }
   InitArgs ia{};

@@ -195,7 +195,7 @@ struct ChainInit {
   bool refresh_only;       // only recompute the cached log-det / rss at the current lambda
 };
 void launch_chain_init(const DeviceData &dd, const Priors &pr, const ChainState &cs, const ChainInit &ci, cudaStream_t s);
-// nrep > 1: that many iterations in one launch (only with chain_step_loops(): the general kernel, fixed Gram matrix)
+// nrep > 1: that many iterations in one launch (only with chain_step_loops(): fixed Gram matrix, i.e. cached statistics)
 void launch_chain_step(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl *ctl, double *draws,
                        cudaStream_t s, int nrep = 1);
 bool chain_step_loops(const DeviceData &dd, const Priors &pr);

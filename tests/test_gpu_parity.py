@@ -160,9 +160,10 @@ def test_general_chain_step_wide_designs(model, prior, k):
     assert relnorm(got, ref) < 1e-7
 
 
-@pytest.mark.parametrize("model,prior,k", [("sar", "Horseshoe", 14), ("lm", "Shrinkage", 12), ("sem", "Conjugate", 5)])
+@pytest.mark.parametrize("model,prior,k", [("sar", "Horseshoe", 14), ("lm", "Shrinkage", 12), ("sem", "Conjugate", 5),
+                                           ("sem", "Independent", 20), ("sar", "Independent", 5), ("lm", "Independent", 28)])
 def test_looped_chain_kernel_equals_one_launch_per_step(model, prior, k, monkeypatch):
-    """With cached statistics the general chain kernel runs a whole block of iterations in one launch (csrc/chain.cu, nrep):
+    """With cached statistics the chain kernels (general and fast) run a whole block of iterations in one launch (csrc/chain.cu, nrep):
     the draws must be bit-identical to one launch per step (BSREG_NO_CHAIN_LOOP), to the streamed run (the sweeps
     recompute the same Gram matrix), and must not depend on how the run is cut into blocks."""
     from bsreg_b200 import capi
