@@ -299,7 +299,7 @@ static cudaError_t launch_persistent_checked(bsreg_handle *h, Shard &s, const Ru
   if (e != cudaSuccess) return e;
   const char *force = getenv("BSREG_FORCE_COOP_FAIL");             // test hook: behave as if the launch had been refused
   if (force && *force == '1') e = cudaErrorCooperativeLaunchTooLarge;
-  else e = launch_persistent(s.dd, h->pr, s.cs, ctl, s.draws_dev, count, cached, s.psync, s.sm_count, s.stream);
+  else e = launch_persistent(s.dd, h->pr, s.cs, ctl, s.ctl_dev, s.draws_dev, count, cached, s.psync, s.sm_count, s.stream);
   if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
     // the buffers were cleared: rebuild the Gram matrix the one-launch path expects (one sweep into buffer 0)
     cudaGetLastError();
@@ -314,7 +314,7 @@ int enqueue_iterations_delta(bsreg_handle *h, Shard &s, int count);
 int enqueue_iterations(bsreg_handle *h, Shard &s, int count, const RunCtl &ctl) {
   if (s.dl.L > 0) return enqueue_iterations_delta(h, s, count);
   const bool streamed = h->stats_mode == BSREG_STATS_STREAM;
-  if (count >= 3 && !s.no_coop && persistent_supported(s.dd, h->pr, s.cs.n_chains, s.sm_count)) {
+  if (count >= 3 && !s.no_coop && persistent_supported(s.dd, h->pr, s.cs.n_chains, s.sm_count, streamed)) {
     // one cooperative launch for the whole block: sweep CTAs and chain CTAs meet at the triple-buffered Gram matrix
     const size_t gbytes = (size_t)3 * h->d * h->d * 8;
     const cudaError_t le = launch_persistent_checked(h, s, ctl, count, !streamed, gbytes);

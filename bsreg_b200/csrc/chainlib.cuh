@@ -24,7 +24,9 @@ __device__ __forceinline__ double warp_sum_c(double v) {
 
 template <int NT>
 __device__ __forceinline__ void bsync() {
-  if (NT == 32) __syncwarp(); else __syncthreads();
+  // a named barrier over the chain's NT threads (threads 0 .. NT - 1 of the CTA): the same code runs as a kernel of NT threads
+  // and inside the chain CTAs of the persistent kernel, whose other warps have retired
+  if (NT == 32) __syncwarp(); else asm volatile("bar.sync 15, %0;\n" ::"n"(NT) : "memory");
 }
 
 // fixed-order block sum, result in every thread
@@ -32,9 +34,9 @@ template <int NT>
 __device__ __forceinline__ double bsum(double v, double *red) {
   v = warp_sum_c(v);
   if (NT == 32) return v;
-  __syncthreads();
+  bsync<NT>();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
+  bsync<NT>();
   double s = 0.0;
 #pragma unroll
   for (int w = 0; w < NT / 32; ++w) s += red[w];
@@ -239,11 +241,11 @@ __device__ __forceinline__ Work carve(double *sm, int m, int model) {
 
 // copy the Gram matrix of this launch's buffer into shared memory (both triangles)
 template <int NT>
-__device__ __forceinline__ void stage_gram(const DeviceData &dd, double *Gs) {
+__device__ __forceinline__ void stage_gram(const DeviceData &dd, double *Gs, int chain) {
   if (Gs == nullptr) return;
   const int d = dd.d;
   if (dd.Gchain != nullptr) {                             // sampled delta: the chain's own Gram matrix (chain = CTA)
-    const double *gc = dd.Gchain + (size_t)blockIdx.x * d * d;
+    const double *gc = dd.Gchain + (size_t)chain * d * d;
     for (int e = threadIdx.x; e < d * d; e += NT) Gs[e] = gc[e];
     return;
   }

@@ -94,7 +94,8 @@ struct DeltaData {
 // entry (i, j) of the Gram matrix from the fixed-point buffer of this launch
 __device__ __forceinline__ double g_load(const DeviceData &dd, int i, int j) {
   const int e = i <= j ? i * dd.d + j : j * dd.d + i;
-  return (double)dd.Gfix[(size_t)dd.gcur * dd.d * dd.d + e] * dd.Gscale[e];
+  // through L2: inside the persistent kernel the buffer is rewritten by the sweep CTAs' atomics behind L1's back
+  return (double)__ldcg(dd.Gfix + (size_t)dd.gcur * dd.d * dd.d + e) * dd.Gscale[e];
 }
 
 struct Priors {
@@ -200,10 +201,10 @@ void launch_chain_step(const DeviceData &dd, const Priors &pr, const ChainState 
                        cudaStream_t s, int nrep = 1);
 bool chain_step_loops(const DeviceData &dd, const Priors &pr);
 // launchers (persist.cu)
-bool persistent_supported(const DeviceData &dd, const Priors &pr, int n_chains, int sm_count);
+bool persistent_supported(const DeviceData &dd, const Priors &pr, int n_chains, int sm_count, bool streamed);
 size_t persistent_sync_bytes();
-cudaError_t launch_persistent(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl &ctl, double *draws,
-                              int K, bool cached, void *sync, int sm_count, cudaStream_t s);
+cudaError_t launch_persistent(const DeviceData &dd, const Priors &pr, const ChainState &cs, const RunCtl &ctl, const RunCtl *ctl_dev,
+                              double *draws, int K, bool cached, void *sync, int sm_count, cudaStream_t s);
 
 void launch_eval_logdet(const DeviceData &dd, int n_eval, const double *v, double *out, cudaStream_t s);
 void launch_eval_conditionals(const DeviceData &dd, const Priors &pr, const double *mu0, int n_eval, const double *beta,

@@ -19,6 +19,7 @@ for model in models:
                              ldet=capi.LDET_CHEBYSHEV if model != "lm" else capi.LDET_NONE, cheb_order=50, cheb_probes=8,
                              n_chains=64, seed=1, stats_mode=mode, sng=dict(theta_scale=0.3) if prior == capi.PRIOR_SHRINKAGE else None) as h:
                 h.run(240, 0)
+                h.run(0, 480)                 # the draw buffers exist before the timed run
                 h.sync()
                 t0 = time.perf_counter()
                 d = h.run(0, 480)
