@@ -221,6 +221,26 @@ def test_priors_in_the_persistent_kernel(model, prior, k, n, monkeypatch):
     assert relnorm(got[3].T, ref) < 1e-7
 
 
+@pytest.mark.parametrize("model,n,k", [("lm", 50, 1), ("sar", 50, 1), ("sem", 65, 2), ("sar", 129, 3), ("sem", 31, 1)])
+def test_tiny_problems(model, n, k):
+    """Edge of the tiling: fewer rows than one 64-row tile, one row beyond a tile boundary, a single regressor.  Gram matrix
+    and a short trajectory against the oracle."""
+    p = small_problem(model, n=n, k=k, knn=4)
+    with cuda_handle(model, p, seed=3, n_chains=2) as h:
+        G = h.eval_gram()
+        got = h.run(20, 30)[1].T
+    Wy = core.spmm(p.W, p.y) if model != "lm" else None
+    WX = core.spmm(p.W, p.X) if model == "sem" else None
+    G_ref = core.gram(p.y, p.X, Wy, WX)
+    if model == "lm":                                   # the device matrix keeps an (empty) Wy slot
+        keep = [0] + list(range(2, 2 + k))
+        G = G[np.ix_(keep, keep)]
+    scale = np.sqrt(np.outer(np.diag(G_ref), np.diag(G_ref)))
+    assert np.max(np.abs(G - G_ref) / scale) < 1e-13
+    ref = oracle_draws(oracle_chain(model, p, seed=3, chain=1), 30, 20)
+    assert got.shape == ref.shape and relnorm(got, ref) < 1e-7
+
+
 @pytest.mark.parametrize("model,own_psi", [("slx", False), ("sdm", False), ("sdm", True), ("sdem", False), ("sdem", True)])
 def test_slx_family_with_fixed_connectivity(model, own_psi):
     """SLX / SDM / SDEM (R/40_setup.R:99-120): X <- [X, Psi_SLX %*% X_SLX] at set-up (R/12_slx.R:60-68), Psi_SLX = the model's W by
