@@ -345,12 +345,19 @@ def run_ours(args):
         roof = {"kernel": "gibbs_persistent_kernel<4, mma>: 126 sweep CTAs (TMA-fed fused CSR SpMV + Gram reduction on the FP64 "
                           "tensor cores, one pass over W, y, X per Gibbs iteration) + 22 chain CTAs (3 chains each), one "
                           "cooperative launch per step",
-                "bound": "l2/issue (operands L2-resident)", "achieved": in_loop, "peak": hbm_peak, "unit": "GB/s",
+                "bound": "chain step (dependent FP64 arithmetic); operands L2-resident, sweep side at 0.38 of the L2 roof",
+                "achieved": in_loop, "peak": hbm_peak, "unit": "GB/s",
                 "frac": in_loop / hbm_peak,
                 "frac_is": "ALGORITHMIC bytes (W, y, X once per Gibbs iteration, SURVEY 8d) / launch time / measured HBM copy "
                            "peak.  At cfg4 the 29 MB of operands stay in L2 inside a launch, so this is NOT a fraction of an "
-                           "HBM roofline (it could exceed 1): the iteration is max(sweep on the L2 -> SM path, chain step "
-                           "bound by instruction issue).  The HBM-bound evidence is hbm_bound_check (same kernel, N = 1e6)",
+                           "HBM roofline (it could exceed 1): the iteration is max(sweep side, chain step).  The HBM-bound "
+                           "evidence is hbm_bound_check (same kernel, N = 1e6)",
+                "inloop_l2": {"l2_to_sm_peak_GBps": 18400.0, "l2_to_sm_peak_source": "profiles/r2_micro_l2_bandwidth.log "
+                              "(bulk copies, 29 MB working set; 16-byte loads: 16900)",
+                              "l2_traffic_GBps": 6950.0, "l2_to_sm_read_MB_per_iteration": 34.0, "frac_of_l2_peak": 0.38,
+                              "source": "profiles/r2_persistent_inloop_metrics.txt: ncu single-pass counters of one "
+                                        "500-iteration launch, build b564a8a (the persistent kernel has not changed since); "
+                                        "recorded figures, not measured in this run"},
                 "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes": bytes_sweep * ITERS_PER_STEP,
                 "algorithmic_bytes_per_iteration": bytes_sweep, "peak_source": peak_src,
