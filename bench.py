@@ -345,7 +345,7 @@ def run_ours(args):
         roof = {"kernel": "gibbs_persistent_kernel<4, mma>: 126 sweep CTAs (TMA-fed fused CSR SpMV + Gram reduction on the FP64 "
                           "tensor cores, one pass over W, y, X per Gibbs iteration) + 22 chain CTAs (3 chains each), one "
                           "cooperative launch per step",
-                "bound": "chain step (dependent FP64 arithmetic); operands L2-resident, sweep side at 0.38 of the L2 roof",
+                "bound": "l2/issue (operands L2-resident): the chain step binds, the sweep side runs at 0.38 of the L2 roof",
                 "achieved": in_loop, "peak": hbm_peak, "unit": "GB/s",
                 "frac": in_loop / hbm_peak,
                 "frac_is": "ALGORITHMIC bytes (W, y, X once per Gibbs iteration, SURVEY 8d) / launch time / measured HBM copy "
