@@ -12,7 +12,9 @@ from oracle.sampler import NumpyRNG, RefChain, sample
 pytestmark = pytest.mark.gpu
 
 CASES = [("sar", "Independent", 5), ("sem", "Independent", 5), ("sar", "Horseshoe", 6), ("lm", "Shrinkage", 6),
-         ("sar", "Independent", 14)]          # the last one runs the persistent kernel (d = 16)
+         ("sar", "Independent", 14),          # runs the persistent kernel (d = 16)
+         ("lm", "Conjugate", 14),             # the general chain step inside the persistent kernel
+         ("sar", "Shrinkage", 13)]            # four-warp general chain kernel, two factorisations per iteration
 
 
 @pytest.mark.parametrize("model,prior,k", CASES)
